@@ -1,0 +1,541 @@
+// adm_scale<S> / adm_rows_finish -- integer ADM at 4 scales (replaces libvmaf integer_adm.c, reached
+// from the reference at app/vmaf_analyzer.py:417; algorithm: SURVEY.md Appendix A.4).
+//
+// One fused kernel per scale: db2 DWT (vertical then horizontal, MIRROR borders, libvmaf's
+// per-scale shifts) of the ref and dis tile -> band_a written for the next scale; h/v/d bands stay
+// on chip -> decouple (Q15 reciprocal LUT, 1-degree angle test, enhancement-gain limit) -> CSF
+// weighting -> 3x3 contrast-masking threshold -> cubed numerator, and the cubed CSF denominator of
+// the reference bands.  libvmaf rounds its accumulators once per image ROW, so the kernel produces
+// exact per-row 64-bit sums (warp shuffle -> shared -> one global atomic per row/band/CTA) and
+// adm_rows_finish applies the row shift and adds the rows.  All arithmetic is integer except the
+// angle test and the gain limit, which follow the C promotion rules in IEEE double (no FMA).
+//
+// CTA = 64x16 band pixels (+1 halo for the 3x3 threshold) = 134x38 input samples per picture.
+#include "bv_common.cuh"
+#include "../../include/b200vmaf.h"
+#include <math.h>
+
+namespace {
+
+constexpr int AT_W = 64, AT_H = 16, AT_THREADS = 256;
+constexpr int AP_W = AT_W + 2, AP_H = AT_H + 2;          // band positions incl. the contrast-masking halo
+constexpr int AN_C = 2 * AT_W + 6, AN_R = 2 * AT_H + 6;  // staged input samples
+constexpr int AN_P = AN_C + 2;                           // shared-memory pitch (elements)
+constexpr int A_RING = 2 * AP_W + 2 * AT_H;              // halo-only positions
+
+__constant__ int c_dwt_lo[4] = { 15826, 27411, 7345, -4240 };
+__constant__ int c_dwt_hi[4] = { -4240, -7345, 27411, -15826 };
+constexpr int DWT_LO_SUM = 46342;
+
+struct AdmArgs {
+    BvPlane ref, dis;                // input of this scale (picture or previous band_a)
+    void *a_ref, *a_dis;             // band_a outputs, frame f at + f * a_frame_elems (unused at scale 3)
+    size_t a_frame_elems;
+    BvAdmScaleParams sp;
+    int bpc;
+    const int *div_lookup;
+    double egl;
+    float cos_1deg_sq;
+    unsigned long long *rows;        // [frame][rows_frame_stride]; this scale at + rows_offset: [row][6]
+    size_t rows_frame_stride, rows_offset;
+};
+
+template <int SCALE> struct AdmTypes;
+template <> struct AdmTypes<0> { using Stage = uint16_t; using V = short4; using Out = int16_t; };
+template <> struct AdmTypes<1> { using Stage = int16_t;  using V = int4;   using Out = int32_t; };
+template <> struct AdmTypes<2> { using Stage = int32_t;  using V = int4;   using Out = int32_t; };
+template <> struct AdmTypes<3> { using Stage = int32_t;  using V = int4;   using Out = int32_t; };
+
+template <int SCALE> struct AdmShifts {
+    // DWT shifts of scales 1..3 (index SCALE-1); scale 0 uses the picture depth
+    static constexpr int sh_v = SCALE == 1 ? 0 : 16;
+    static constexpr long long rnd_v = SCALE == 1 ? 0 : 32768;
+    static constexpr int sh_h = SCALE == 2 ? 16 : 15;
+    static constexpr long long rnd_h = SCALE == 2 ? 32768 : 16384;
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// Decouple + CSF of one band position.  o/t: reference / distorted (h, v, d).
+// Returns |csf-weighted restored| per band, the 3-band sums of csf_f (neighbour weight 1/30) and of
+// the centre weight (1/15).
+template <int SCALE>
+__device__ __forceinline__ void adm_decouple_csf(const int (&o)[3], const int (&t)[3], const AdmArgs &a,
+                                                 int (&xabs)[3], int &cfsum, int &ccsum)
+{
+    const long long ot_dp = (long long)o[0] * t[0] + (long long)o[1] * t[1];
+    const long long o_mag = (long long)o[0] * o[0] + (long long)o[1] * o[1];
+    const long long t_mag = (long long)t[0] * t[0] + (long long)t[1] * t[1];
+    const double fa = (double)__ll2float_rn(ot_dp) * (1.0 / 4096.0);
+    const double fo = (double)__ll2float_rn(o_mag) * (1.0 / 4096.0);
+    const double ft = (double)__ll2float_rn(t_mag) * (1.0 / 4096.0);
+    const bool flag = (fa >= 0.0) &&
+                      (__dmul_rn(fa, fa) >= __dmul_rn(__dmul_rn((double)a.cos_1deg_sq, fo), ft));
+    unsigned cf_acc = 0, cc_acc = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const int ob = o[b], tb = t[b];
+        int k;
+        if (ob == 0) {
+            k = 32768;
+        } else if (SCALE == 0) {
+            const int tmp = (int)(((long long)__ldg(a.div_lookup + ob + 32768) * tb + 16384) >> 15);
+            k = clampi(tmp, 0, 32768);
+        } else {
+            const unsigned ao = (unsigned)abs(ob);
+            unsigned msb = ao;
+            int sh = 0;
+            if (ao >= 32768u) {
+                sh = 17 - __clz(ao);
+                msb = (ao + (1u << (sh - 1))) >> sh;
+            }
+            long long prod = (long long)__ldg(a.div_lookup + msb + 32768) * tb;
+            if (ob < 0) prod = -prod;
+            const long long tmp = (prod + (1ll << (14 + sh))) >> (15 + sh);
+            k = (int)(tmp < 0 ? 0 : (tmp > 32768 ? 32768 : tmp));
+        }
+        int rst = (int)(((long long)k * ob + 16384) >> 15);
+        if (SCALE == 0) rst = (short)rst;
+        if (flag && k > 0) {
+            const double v = __dmul_rn((double)rst, a.egl), tt = (double)tb;
+            if (ob > 0) rst = __double2int_rz(v < tt ? v : tt);
+            else rst = __double2int_rz(v > tt ? v : tt);
+        }
+        if (SCALE == 0) rst = (short)rst;
+        int ad = tb - rst;
+        if (SCALE == 0) ad = (short)ad;
+        int ca, x;
+        if (SCALE == 0) {
+            const int sh = b == 2 ? 17 : 15;
+            const int dv = (int)(a.sp.rf[b] * (unsigned)ad);
+            ca = (short)((dv + (1 << (sh - 1))) >> sh);
+            cf_acc += (unsigned)(int)(short)((4369 * abs(ca) + 2048) >> 12);
+            cc_acc += (unsigned)(int)(short)((8738 * abs(ca) + 2048) >> 12);
+            x = (int)((unsigned)rst * a.sp.rf[b]);
+        } else {
+            ca = (int)(((long long)a.sp.rf[b] * (long long)ad + (1ll << 27)) >> 28);
+            cf_acc += (unsigned)(int)((143165577ll * abs(ca) + (1ll << 31)) >> 32);
+            cc_acc += (unsigned)(int)((286331153ll * abs(ca) + (1ll << 31)) >> 32);
+            x = (int)(((long long)rst * (long long)a.sp.rf[b] + (1ll << 27)) >> 28);
+        }
+        xabs[b] = abs(x);
+    }
+    cfsum = (int)cf_acc;
+    ccsum = (int)cc_acc;
+}
+
+template <int SCALE, typename TIn>
+__global__ void __launch_bounds__(AT_THREADS)
+adm_scale_kernel(BvBatch batch, AdmArgs a)
+{
+    using Stage = typename AdmTypes<SCALE>::Stage;
+    using VT = typename AdmTypes<SCALE>::V;
+    using Out = typename AdmTypes<SCALE>::Out;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    VT *s_v = reinterpret_cast<VT *>(smem);                                          // [AP_H][AN_P]
+    int *s_cf = reinterpret_cast<int *>(smem + sizeof(VT) * AP_H * AN_P);            // [AP_H][AP_W]
+    int *s_x = s_cf + AP_H * AP_W;                                                   // [3][AT_H*AT_W]
+    int *s_cc = s_x + 3 * AT_H * AT_W;                                               // [AT_H*AT_W]
+    unsigned long long *s_row = reinterpret_cast<unsigned long long *>(s_cc + AT_H * AT_W);   // [AT_H][6]
+    Stage *s_in = reinterpret_cast<Stage *>(s_row + AT_H * 6);                       // [2][AN_R][AN_P]
+
+    const int f = blockIdx.z;
+    if (batch.flags[f] & (BV_FRAME_LEAD_IN | BV_FRAME_SKIP_SPATIAL)) return;
+
+    const int in_w = a.sp.in_w, in_h = a.sp.in_h, ow = a.sp.w, oh = a.sp.h;
+    const int tx0 = blockIdx.x * AT_W, ty0 = blockIdx.y * AT_H;
+    const int cx0 = 2 * tx0 - 3, ry0 = 2 * ty0 - 3;
+    const int tid = threadIdx.x;
+
+    if (tid < AT_H * 6) s_row[tid] = 0ull;
+
+    // ---- phase A: stage the input tile of both pictures (MIRROR resolved, far overhang clamped) ----
+    {
+        const uint8_t *pr = a.ref.p[f], *pd = a.dis.p[f];
+        for (int idx = tid; idx < AN_R * AN_C; idx += AT_THREADS) {
+            const int r = idx / AN_C, c = idx - r * AN_C;
+            const int gy = bv_mirror(clampi(ry0 + r, -(in_h - 1), 2 * in_h - 1), in_h);
+            const int gx = bv_mirror(clampi(cx0 + c, -(in_w - 1), 2 * in_w - 1), in_w);
+            s_in[r * AN_P + c] = (Stage)__ldg(reinterpret_cast<const TIn *>(pr + (size_t)gy * a.ref.pitch) + gx);
+            s_in[(AN_R + r) * AN_P + c] = (Stage)__ldg(reinterpret_cast<const TIn *>(pd + (size_t)gy * a.dis.pitch) + gx);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: vertical DWT pass: lo/hi of ref and dis for every band row of the halo tile ----
+    for (int idx = tid; idx < AP_H * AN_C; idx += AT_THREADS) {
+        const int r = idx / AN_C, c = idx - r * AN_C;
+        const int bi = bv_mirror(clampi(ty0 - 1 + r, -1, oh), oh);
+        int rk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rk[k] = clampi(bv_mirror(2 * bi - 1 + k, in_h) - ry0, 0, AN_R - 1);
+        VT out;
+        if (SCALE == 0) {
+            const int add_v = 1 << (a.bpc - 1);
+            int lo_r = 0, hi_r = 0, lo_d = 0, hi_d = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xr = (int)s_in[rk[k] * AN_P + c], xd = (int)s_in[(AN_R + rk[k]) * AN_P + c];
+                lo_r += c_dwt_lo[k] * xr; hi_r += c_dwt_hi[k] * xr;
+                lo_d += c_dwt_lo[k] * xd; hi_d += c_dwt_hi[k] * xd;
+            }
+            lo_r -= DWT_LO_SUM * add_v; lo_d -= DWT_LO_SUM * add_v;
+            out.x = (short)((lo_r + add_v) >> a.bpc); out.y = (short)((hi_r + add_v) >> a.bpc);
+            out.z = (short)((lo_d + add_v) >> a.bpc); out.w = (short)((hi_d + add_v) >> a.bpc);
+        } else {
+            long long lo_r = 0, hi_r = 0, lo_d = 0, hi_d = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long xr = (long long)s_in[rk[k] * AN_P + c], xd = (long long)s_in[(AN_R + rk[k]) * AN_P + c];
+                lo_r += c_dwt_lo[k] * xr; hi_r += c_dwt_hi[k] * xr;
+                lo_d += c_dwt_lo[k] * xd; hi_d += c_dwt_hi[k] * xd;
+            }
+            constexpr int sh = AdmShifts<SCALE>::sh_v;
+            constexpr long long rnd = AdmShifts<SCALE>::rnd_v;
+            out.x = (int)((lo_r + rnd) >> sh); out.y = (int)((hi_r + rnd) >> sh);
+            out.z = (int)((lo_d + rnd) >> sh); out.w = (int)((hi_d + rnd) >> sh);
+        }
+        s_v[r * AN_P + c] = out;
+    }
+    __syncthreads();
+
+    // ---- phase C: horizontal DWT pass + decouple + CSF for every position (interior first) ----
+    const int left = a.sp.left, top = a.sp.top, right = a.sp.right, bottom = a.sp.bottom;
+    const int gl = max(left - 1, 0), gt = max(top - 1, 0), gr = min(right + 1, ow), gb = min(bottom + 1, oh);
+#pragma unroll 1
+    for (int p = tid; p < AT_H * AT_W + A_RING; p += AT_THREADS) {
+        const bool interior = p < AT_H * AT_W;         // warp-uniform (AT_H*AT_W is a multiple of 32)
+        int r, c;
+        if (interior) {
+            r = p / AT_W + 1; c = p % AT_W + 1;
+        } else {
+            const int q = p - AT_H * AT_W;
+            if (q < AP_W) { r = 0; c = q; }
+            else if (q < 2 * AP_W) { r = AP_H - 1; c = q - AP_W; }
+            else { r = 1 + ((q - 2 * AP_W) >> 1); c = ((q - 2 * AP_W) & 1) ? AP_W - 1 : 0; }
+        }
+        const int bi_raw = ty0 - 1 + r, bj_raw = tx0 - 1 + c;
+        const bool valid = bi_raw >= -1 && bi_raw <= oh && bj_raw >= -1 && bj_raw <= ow;
+        const int bi = bv_mirror(clampi(bi_raw, -1, oh), oh), bj = bv_mirror(clampi(bj_raw, -1, ow), ow);
+        const bool in_img = bi_raw < oh && bj_raw < ow;            // interior positions only
+        const bool in_g = valid && bi >= gt && bi < gb && bj >= gl && bj < gr;
+        const bool core = interior && in_img && bi >= top && bi < bottom && bj >= left && bj < right;
+
+        unsigned long long dsum[3] = { 0ull, 0ull, 0ull };
+        int cfsum = 0;
+        if (in_g || (interior && in_img && SCALE < 3)) {
+            VT tv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                tv[k] = s_v[r * AN_P + clampi(bv_mirror(2 * bj - 1 + k, in_w) - cx0, 0, AN_C - 1)];
+            if (SCALE < 3 && interior && in_img) {
+                Out ar, ad;
+                if (SCALE == 0) {
+                    int s_r = 0, s_d = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { s_r += c_dwt_lo[k] * (int)tv[k].x; s_d += c_dwt_lo[k] * (int)tv[k].z; }
+                    ar = (Out)((s_r + 32768) >> 16); ad = (Out)((s_d + 32768) >> 16);
+                } else {
+                    long long s_r = 0, s_d = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { s_r += (long long)c_dwt_lo[k] * tv[k].x; s_d += (long long)c_dwt_lo[k] * tv[k].z; }
+                    ar = (Out)((s_r + AdmShifts<SCALE>::rnd_h) >> AdmShifts<SCALE>::sh_h);
+                    ad = (Out)((s_d + AdmShifts<SCALE>::rnd_h) >> AdmShifts<SCALE>::sh_h);
+                }
+                const size_t off = (size_t)f * a.a_frame_elems + (size_t)bi * ow + bj;
+                static_cast<Out *>(a.a_ref)[off] = ar;
+                static_cast<Out *>(a.a_dis)[off] = ad;
+            }
+            if (in_g) {
+                int o[3], t[3];       // (h, v, d): h = lo_H(hi_V), v = hi_H(lo_V), d = hi_H(hi_V)
+                if (SCALE == 0) {
+                    int oh_ = 0, ov_ = 0, od_ = 0, th_ = 0, tv_ = 0, td_ = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        oh_ += c_dwt_lo[k] * (int)tv[k].y; ov_ += c_dwt_hi[k] * (int)tv[k].x; od_ += c_dwt_hi[k] * (int)tv[k].y;
+                        th_ += c_dwt_lo[k] * (int)tv[k].w; tv_ += c_dwt_hi[k] * (int)tv[k].z; td_ += c_dwt_hi[k] * (int)tv[k].w;
+                    }
+                    o[0] = (short)((oh_ + 32768) >> 16); o[1] = (short)((ov_ + 32768) >> 16); o[2] = (short)((od_ + 32768) >> 16);
+                    t[0] = (short)((th_ + 32768) >> 16); t[1] = (short)((tv_ + 32768) >> 16); t[2] = (short)((td_ + 32768) >> 16);
+                } else {
+                    long long oh_ = 0, ov_ = 0, od_ = 0, th_ = 0, tv_ = 0, td_ = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        oh_ += (long long)c_dwt_lo[k] * tv[k].y; ov_ += (long long)c_dwt_hi[k] * tv[k].x; od_ += (long long)c_dwt_hi[k] * tv[k].y;
+                        th_ += (long long)c_dwt_lo[k] * tv[k].w; tv_ += (long long)c_dwt_hi[k] * tv[k].z; td_ += (long long)c_dwt_hi[k] * tv[k].w;
+                    }
+                    constexpr int sh = AdmShifts<SCALE>::sh_h;
+                    constexpr long long rnd = AdmShifts<SCALE>::rnd_h;
+                    o[0] = (int)((oh_ + rnd) >> sh); o[1] = (int)((ov_ + rnd) >> sh); o[2] = (int)((od_ + rnd) >> sh);
+                    t[0] = (int)((th_ + rnd) >> sh); t[1] = (int)((tv_ + rnd) >> sh); t[2] = (int)((td_ + rnd) >> sh);
+                }
+                int xabs[3], ccsum;
+                adm_decouple_csf<SCALE>(o, t, a, xabs, cfsum, ccsum);
+                if (interior) {
+                    const int q = p;
+                    s_x[q] = xabs[0]; s_x[AT_H * AT_W + q] = xabs[1]; s_x[2 * AT_H * AT_W + q] = xabs[2];
+                    s_cc[q] = ccsum;
+                }
+                if (core) {
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        if (SCALE == 0) {
+                            const unsigned long long v = (unsigned long long)(uint16_t)abs(o[b]);
+                            dsum[b] = v * v * v;
+                        } else {
+                            const unsigned long long v = (unsigned long long)(unsigned)abs(o[b]);
+                            dsum[b] = ((((v * v + a.sp.den_add_sq) >> a.sp.den_sh_sq) * v) + a.sp.den_add_cub) >> a.sp.den_sh_cub;
+                        }
+                    }
+                }
+            }
+        }
+        s_cf[r * AP_W + c] = cfsum;
+        if (interior && __any_sync(0xffffffffu, core)) {
+            // a warp covers 32 consecutive interior columns of one tile row
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const unsigned long long s = bv_warp_sum(dsum[b]);
+                if ((tid & 31) == 0 && s) atomicAdd(&s_row[(r - 1) * 6 + 3 + b], s);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase D: 3x3 contrast-masking threshold and the cubed numerator ----
+#pragma unroll 1
+    for (int p = tid; p < AT_H * AT_W; p += AT_THREADS) {
+        const int r = p / AT_W + 1, c = p % AT_W + 1;
+        const int bi = ty0 - 1 + r, bj = tx0 - 1 + c;
+        const bool core = bi >= top && bi < bottom && bj >= left && bj < right && bi < oh && bj < ow;
+        if (!__any_sync(0xffffffffu, core)) continue;
+        long long val[3] = { 0, 0, 0 };
+        if (core) {
+            unsigned thr = 0;
+#pragma unroll
+            for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+                for (int dc = -1; dc <= 1; ++dc) thr += (unsigned)s_cf[(r + dr) * AP_W + c + dc];
+            thr = thr - (unsigned)s_cf[r * AP_W + c] + (unsigned)s_cc[p];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                int x = s_x[b * AT_H * AT_W + p] - (int)(thr << a.sp.sh_sub[b]);
+                x = max(x, 0);
+                const int x_sq = (int)(((long long)x * x + (long long)a.sp.add_sq[b]) >> a.sp.sh_sq[b]);
+                val[b] = ((long long)x_sq * x + (long long)a.sp.add_cub[b]) >> a.sp.sh_cub[b];
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const long long s = bv_warp_sum(val[b]);
+            if ((tid & 31) == 0 && s) atomicAdd(&s_row[(r - 1) * 6 + b], (unsigned long long)s);
+        }
+    }
+    __syncthreads();
+    if (tid < AT_H * 6) {
+        const int rr = tid / 6, k = tid - rr * 6;
+        const unsigned long long s = s_row[tid];
+        if (s && ty0 + rr < oh)
+            atomicAdd(a.rows + (size_t)f * a.rows_frame_stride + a.rows_offset + (size_t)(ty0 + rr) * 6 + k, s);
+    }
+}
+
+template <int SCALE> size_t adm_smem()
+{
+    return sizeof(typename AdmTypes<SCALE>::V) * AP_H * AN_P + sizeof(int) * (AP_H * AP_W + 4 * AT_H * AT_W) +
+           sizeof(unsigned long long) * AT_H * 6 + sizeof(typename AdmTypes<SCALE>::Stage) * 2 * AN_R * AN_P;
+}
+
+struct AdmFinishArgs {
+    BvAdmScaleParams sp[4];
+    const unsigned long long *rows;
+    size_t rows_frame_stride, rows_offset[4];
+    unsigned long long *raw;
+};
+
+// libvmaf's per-row rounding: cm += (row_sum + add) >> shift, same for the denominator.
+__global__ void __launch_bounds__(128)
+adm_rows_finish_kernel(BvBatch batch, AdmFinishArgs a)
+{
+    __shared__ long long scratch[6 * 32];
+    const int scale = blockIdx.x, f = blockIdx.y;
+    if (batch.flags[f] & (BV_FRAME_LEAD_IN | BV_FRAME_SKIP_SPATIAL)) return;
+    const BvAdmScaleParams &sp = a.sp[scale];
+    const unsigned long long *rows = a.rows + (size_t)f * a.rows_frame_stride + a.rows_offset[scale];
+    long long acc[6] = { 0, 0, 0, 0, 0, 0 };
+    for (int i = sp.top + (int)threadIdx.x; i < sp.bottom; i += blockDim.x) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            acc[b] += (long long)((rows[(size_t)i * 6 + b] + sp.add_inner) >> sp.sh_inner);
+            acc[3 + b] += (long long)((rows[(size_t)i * 6 + 3 + b] + sp.den_add_row) >> sp.den_sh_row);
+        }
+    }
+    long long cmv[3] = { acc[0], acc[1], acc[2] }, dnv[3] = { acc[3], acc[4], acc[5] };
+    bv_block_accumulate<3>(cmv, scratch, a.raw + (size_t)f * BV_RAW_WORDS + BV_RAW_ADM_CM + 3 * scale);
+    __syncthreads();
+    bv_block_accumulate<3>(dnv, scratch, a.raw + (size_t)f * BV_RAW_WORDS + BV_RAW_ADM_DEN + 3 * scale);
+}
+
+template <int SCALE, typename TIn>
+void launch_scale(const BvBatch &b, const AdmArgs &a, cudaStream_t st)
+{
+    static bool configured = false;
+    const size_t smem = adm_smem<SCALE>();
+    if (!configured) {
+        cudaFuncSetAttribute(adm_scale_kernel<SCALE, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    dim3 grid((a.sp.w + AT_W - 1) / AT_W, (a.sp.h + AT_H - 1) / AT_H, b.n);
+    adm_scale_kernel<SCALE, TIn><<<grid, AT_THREADS, smem, st>>>(b, a);
+}
+
+float dwt_quant_step(int lambda, int theta, double view_dist, int display_h)
+{
+    // Watson et al. DWT quantisation model, evaluated the way libvmaf's adm_tools.h does (float
+    // temporaries around double libm calls).
+    static const float amp[4][4] = {
+        { 0.62171f, 0.67234f, 0.72709f, 0.67234f }, { 0.34537f, 0.41317f, 0.49428f, 0.41317f },
+        { 0.18004f, 0.22727f, 0.28688f, 0.22727f }, { 0.091401f, 0.11792f, 0.15214f, 0.11792f } };
+    static const float g[4] = { 1.501f, 1.0f, 0.534f, 1.0f };
+    const float a = 0.495f, k = 0.466f, f0 = 0.401f;
+    float r = view_dist * display_h * M_PI / 180.0;
+    float temp = log10(pow(2.0, lambda + 1) * f0 * g[theta] / r);
+    float Q = 2.0 * a * pow(10.0, k * temp * temp) / amp[lambda][theta];
+    return Q;
+}
+
+}  // namespace
+
+void bv_adm_rfactor(int scale, double view_dist, int display_h, float rf[3])
+{
+    const float f1 = dwt_quant_step(scale, 1, view_dist, display_h);
+    const float f2 = dwt_quant_step(scale, 2, view_dist, display_h);
+    rf[0] = 1.0f / f1; rf[1] = 1.0f / f1; rf[2] = 1.0f / f2;
+}
+
+// Per-scale fixed-point parameters (libvmaf integer_adm.c: i4_adm_cm / adm_csf_den_scale shifts).
+void bv_adm_make_params(int w, int h, double view_dist, int display_h, BvAdmScaleParams sp[4])
+{
+    int cw = w, ch = h;
+    for (int s = 0; s < 4; ++s) {
+        BvAdmScaleParams &p = sp[s];
+        p.in_w = cw; p.in_h = ch;
+        cw = (cw + 1) / 2; ch = (ch + 1) / 2;
+        p.w = cw; p.h = ch;
+        p.left = (int)(cw * 0.1 - 0.5); p.top = (int)(ch * 0.1 - 0.5);
+        p.right = cw - p.left; p.bottom = ch - p.top;
+        float rf[3];
+        bv_adm_rfactor(s, view_dist, display_h, rf);
+        if (s == 0) {
+            if (fabs(view_dist * display_h - 3.0 * 1080) < 1.0e-8) {
+                p.rf[0] = 36453; p.rf[1] = 36453; p.rf[2] = 49417;
+            } else {
+                p.rf[0] = (uint16_t)(rf[0] * pow(2, 21)); p.rf[1] = (uint16_t)(rf[1] * pow(2, 21));
+                p.rf[2] = (uint16_t)(rf[2] * pow(2, 23));
+            }
+            p.sh_sub[0] = 10; p.sh_sub[1] = 10; p.sh_sub[2] = 12;
+            p.sh_sq[0] = 29; p.sh_sq[1] = 29; p.sh_sq[2] = 30;
+            p.sh_cub[0] = p.sh_cub[1] = (int)(uint32_t)ceil(log2(cw) - 4);
+            p.sh_cub[2] = (int)(uint32_t)ceil(log2(cw) - 3);
+        } else {
+            for (int b = 0; b < 3; ++b) {
+                p.rf[b] = (uint32_t)(rf[b] * pow(2, 32));
+                p.sh_sub[b] = 0; p.sh_sq[b] = 30; p.sh_cub[b] = (int)(uint32_t)ceil(log2(cw));
+            }
+        }
+        for (int b = 0; b < 3; ++b) {
+            p.add_sq[b] = 1ull << (p.sh_sq[b] - 1);
+            p.add_cub[b] = (unsigned long long)(uint32_t)pow(2, (p.sh_cub[b] - 1));
+        }
+        p.sh_inner = (int)(uint32_t)ceil(log2(ch));
+        p.add_inner = (unsigned long long)(uint32_t)pow(2, (p.sh_inner - 1));
+        if (s == 0) {
+            int sh_acc = (int)ceil(log2((double)(p.bottom - p.top) * (p.right - p.left)) - 20);
+            if (sh_acc < 0) sh_acc = 0;
+            p.den_sh_row = sh_acc; p.den_add_row = sh_acc > 0 ? (1ull << (sh_acc - 1)) : 0ull;
+            p.den_sh_sq = 0; p.den_add_sq = 0; p.den_sh_cub = 0; p.den_add_cub = 0;
+        } else {
+            static const int sh_sqd[3] = { 31, 30, 31 };
+            p.den_sh_sq = sh_sqd[s - 1]; p.den_add_sq = 1ull << (p.den_sh_sq - 1);
+            p.den_sh_cub = (int)(uint32_t)ceil(log2(p.right - p.left));
+            p.den_add_cub = (unsigned long long)(uint32_t)pow(2, (p.den_sh_cub - 1));
+            p.den_sh_row = (int)(uint32_t)ceil(log2(p.bottom - p.top));
+            p.den_add_row = (unsigned long long)(uint32_t)pow(2, (p.den_sh_row - 1));
+        }
+    }
+}
+
+// Scalar finalisation of one scale (host): integer accumulators -> float num / den as libvmaf
+// stores them (powf on the host libm, float partial sums).
+void bv_adm_finish_scale(const BvAdmScaleParams &p, int scale, double view_dist, int display_h,
+                         const int64_t cm[3], const uint64_t dn[3], float *num_scale, float *den_scale)
+{
+    float rf[3];
+    bv_adm_rfactor(scale, view_dist, display_h, rf);
+    const float area_term = powf((p.bottom - p.top) * (p.right - p.left) / 32.0f, 1.0f / 3.0f);
+    float f_acc[3];
+    if (scale == 0) {
+        f_acc[0] = (float)(cm[0] / pow(2, (52 - p.sh_cub[0] - p.sh_inner)));
+        f_acc[1] = (float)(cm[1] / pow(2, (52 - p.sh_cub[1] - p.sh_inner)));
+        f_acc[2] = (float)(cm[2] / pow(2, (57 - p.sh_cub[2] - p.sh_inner)));
+    } else {
+        static const int fs[3] = { 45, 39, 36 };
+        const float final_shift = pow(2, (fs[scale - 1] - p.sh_cub[0] - p.sh_inner));
+        for (int b = 0; b < 3; ++b) f_acc[b] = (float)(cm[b] / final_shift);
+    }
+    const float nh = powf(f_acc[0], 1.0f / 3.0f) + area_term;
+    const float nv = powf(f_acc[1], 1.0f / 3.0f) + area_term;
+    const float nd = powf(f_acc[2], 1.0f / 3.0f) + area_term;
+    *num_scale = nh + nv + nd;
+
+    double shift_csf;
+    if (scale == 0) {
+        shift_csf = pow(2, (18 - p.den_sh_row));
+    } else {
+        static const int conv[3] = { 32, 27, 23 };
+        shift_csf = pow(2, (conv[scale - 1] - p.den_sh_row - p.den_sh_cub));
+    }
+    float part[3];
+    for (int b = 0; b < 3; ++b) {
+        const double csf = (double)(dn[b] / shift_csf) * pow(rf[b], 3);
+        part[b] = powf(csf, 1.0f / 3.0f) + area_term;
+    }
+    *den_scale = part[0] + part[1] + part[2];
+}
+
+void bv_launch_adm(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, const BvAdmBuffers &ab,
+                   const BvAdmScaleParams sp[4], double egl, unsigned long long *raw, cudaStream_t st,
+                   long long *nlaunch)
+{
+    const float cos_1deg_sq = (float)(cos(1.0 * M_PI / 180.0) * cos(1.0 * M_PI / 180.0));
+    BvPlane cr = ref_y, cd = dis_y;
+    for (int s = 0; s < 4; ++s) {
+        AdmArgs a;
+        a.ref = cr; a.dis = cd;
+        a.a_frame_elems = ab.band_plane_elems[s];
+        const size_t esz = s == 0 ? 2 : 4;
+        a.a_ref = s < 3 ? ab.bands[s] : nullptr;
+        a.a_dis = s < 3 ? static_cast<uint8_t *>(ab.bands[s]) + (size_t)BV_MAX_BATCH * ab.band_plane_elems[s] * esz : nullptr;
+        a.sp = sp[s]; a.bpc = bpc; a.div_lookup = ab.div_lookup; a.egl = egl; a.cos_1deg_sq = cos_1deg_sq;
+        a.rows = ab.rows; a.rows_frame_stride = ab.rows_frame_stride; a.rows_offset = ab.rows_scale_offset[s];
+        switch (s) {
+        case 0:
+            if (bpc == 8) launch_scale<0, uint8_t>(b, a, st); else launch_scale<0, uint16_t>(b, a, st);
+            break;
+        case 1: launch_scale<1, int16_t>(b, a, st); break;
+        case 2: launch_scale<2, int32_t>(b, a, st); break;
+        default: launch_scale<3, int32_t>(b, a, st); break;
+        }
+        ++*nlaunch;
+        if (s < 3) {
+            cr = bv_plane_contig(a.a_ref, (size_t)sp[s].w * esz, ab.band_plane_elems[s] * esz, b.n);
+            cd = bv_plane_contig(a.a_dis, (size_t)sp[s].w * esz, ab.band_plane_elems[s] * esz, b.n);
+        }
+    }
+    AdmFinishArgs fa;
+    for (int s = 0; s < 4; ++s) { fa.sp[s] = sp[s]; fa.rows_offset[s] = ab.rows_scale_offset[s]; }
+    fa.rows = ab.rows; fa.rows_frame_stride = ab.rows_frame_stride; fa.raw = raw;
+    adm_rows_finish_kernel<<<dim3(4, b.n), 128, 0, st>>>(b, fa);
+    ++*nlaunch;
+}

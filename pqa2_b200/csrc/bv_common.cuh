@@ -1,0 +1,151 @@
+// Shared device helpers and the internal kernel-launch interface of libb200vmaf (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define BV_MAX_BATCH 16
+
+// ---- border rules -------------------------------------------------------------------------
+// libvmaf "MIRROR" (motion, ADM DWT, CM neighbourhood): -i -> i ; n+i -> n-1-i
+__device__ __forceinline__ int bv_mirror(int i, int n)
+{
+    if (i < 0) return -i;
+    if (i >= n) return 2 * n - i - 1;
+    return i;
+}
+// integer VIF padding: reflect-101 on all four sides: -i -> i ; n-1+i -> n-1-i
+__device__ __forceinline__ int bv_reflect101(int i, int n)
+{
+    if (i < 0) return -i;
+    if (i >= n) return 2 * (n - 1) - i;
+    return i;
+}
+
+// ---- reductions ---------------------------------------------------------------------------
+__device__ __forceinline__ long long bv_warp_sum(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long bv_warp_sum(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int bv_warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum N per-thread 64-bit values over the block and atomically add them to dst[0..N).
+// scratch: N * 32 long longs of shared memory.
+template <int N>
+__device__ __forceinline__ void bv_block_accumulate(const long long (&v)[N], long long *scratch,
+                                                    unsigned long long *dst)
+{
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        long long s = bv_warp_sum(v[k]);
+        if (lane == 0) scratch[k * 32 + warp] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            long long s = lane < nwarps ? scratch[k * 32 + lane] : 0;
+            s = bv_warp_sum(s);
+            if (lane == 0 && s != 0) atomicAdd(dst + k, (unsigned long long)s);
+        }
+    }
+}
+
+// ---- pixel loads --------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ unsigned bv_ld(const uint8_t *base, size_t pitch, int i, int j)
+{
+    return (unsigned)__ldg(reinterpret_cast<const T *>(base + (size_t)i * pitch) + j);
+}
+
+// ---- launch-parameter blocks (passed by value) --------------------------------------------------
+struct BvBatch {
+    int n;                                  // frames in this launch group
+    unsigned flags[BV_MAX_BATCH];           // BV_FRAME_*
+};
+
+struct BvPlane {                            // one image plane per frame of the group
+    const uint8_t *p[BV_MAX_BATCH];         // frame f of the group (device pointer; zero-copy for bv_submit_device)
+    size_t pitch;                           // bytes per row
+};
+static inline BvPlane bv_plane_contig(const void *base, size_t pitch, size_t frame_stride_bytes, int n)
+{
+    BvPlane pl;
+    for (int f = 0; f < BV_MAX_BATCH; ++f)
+        pl.p[f] = f < n ? static_cast<const uint8_t *>(base) + (size_t)f * frame_stride_bytes : nullptr;
+    pl.pitch = pitch;
+    return pl;
+}
+
+struct BvAdmScaleParams {
+    int in_w, in_h;                         // DWT input dims
+    int w, h;                               // band dims
+    int left, top, right, bottom;           // contrast-masking / denominator region
+    unsigned rf[3];                         // fixed-point csf factors (h, v, d)
+    int sh_sub[3], sh_sq[3], sh_cub[3];     // numerator shifts per band
+    unsigned long long add_sq[3], add_cub[3];
+    int sh_inner; unsigned long long add_inner;   // per-row numerator shift
+    // denominator
+    int den_sh_sq; unsigned long long den_add_sq; // scales 1..3
+    int den_sh_cub; unsigned long long den_add_cub;
+    int den_sh_row; unsigned long long den_add_row;
+};
+
+// ---- kernel launchers (one per .cu file) ---------------------------------------------------
+struct BvLaunchStats { long long launches; };
+
+// motion
+void bv_launch_motion_blur(const BvBatch &b, BvPlane ref_y, int bpc, int w, int h, uint16_t *blur_cur,
+                           size_t blur_frame_elems, cudaStream_t st, long long *nlaunch);
+void bv_launch_motion_sad(const BvBatch &b, const uint16_t *blur_cur, const uint16_t *blur_prev_group_last,
+                          size_t blur_frame_elems, int w, int h, unsigned long long *raw, cudaStream_t st,
+                          long long *nlaunch);
+// vif
+struct BvVifLevels {                        // u16 pyramid levels 1..3 (tight pitch), ref and dis
+    uint16_t *ref[4], *dis[4];              // [0] unused
+    size_t frame_elems[4];
+    int w[4], h[4];
+};
+void bv_launch_vif(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, const BvVifLevels &lv,
+                   const uint16_t *log2_table, double egl, unsigned long long *raw, cudaStream_t st,
+                   long long *nlaunch);
+// adm
+struct BvAdmBuffers {
+    void *bands[4];                         // scale s: [frame][ref/dis][a,v,h,d][h][w], i16 (s=0) / i32
+    size_t band_plane_elems[4];             // w*h of scale s
+    unsigned long long *rows;               // [frame][scale][row][6] row accumulators
+    size_t rows_frame_stride;               // elements between frames
+    size_t rows_scale_offset[4];
+    const int *div_lookup;                  // 65537 entries
+};
+void bv_launch_adm(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, const BvAdmBuffers &ab,
+                   const BvAdmScaleParams sp[4], double egl, unsigned long long *raw, cudaStream_t st,
+                   long long *nlaunch);
+// psnr
+void bv_launch_sse(const BvBatch &b, BvPlane ref, BvPlane dis, int bpc, int w, int h, int plane_idx,
+                   unsigned long long *raw, cudaStream_t st, long long *nlaunch);
+// adm host-side helpers (bv_adm.cu)
+void bv_adm_rfactor(int scale, double view_dist, int display_h, float rf[3]);
+void bv_adm_make_params(int w, int h, double view_dist, int display_h, BvAdmScaleParams sp[4]);
+void bv_adm_finish_scale(const BvAdmScaleParams &p, int scale, double view_dist, int display_h,
+                         const int64_t cm[3], const uint64_t dn[3], float *num_scale, float *den_scale);
+// svr
+void bv_launch_svr(const double *d_feat, int n_feat, const double *d_slopes, const double *d_intercepts,
+                   const double *d_sv, const double *d_coef, int n_sv, double gamma, double rho, double *d_out,
+                   long long n, cudaStream_t st);

@@ -1,0 +1,119 @@
+// motion_blur / motion_sad -- integer motion feature (replaces libvmaf integer_motion.c, reached
+// from the reference at app/vmaf_analyzer.py:417; algorithm: SURVEY.md Appendix A.3).
+//
+// 5-tap Q16 blur {3571,16004,26386,16004,3571}, vertical then horizontal, MIRROR borders,
+// u16 output; SAD against the previous frame's blurred picture.  HBM-bound:
+// reads W*H*bytes (luma) + writes W*H*2 (blur) + SAD reads 2*W*H*2.
+#include "bv_common.cuh"
+#include "../../include/b200vmaf.h"
+
+namespace {
+
+constexpr int MB_TW = 128;   // output tile width
+constexpr int MB_TH = 16;    // output tile height
+constexpr int MB_R = 2;      // filter radius
+
+__constant__ unsigned c_motion_filter[5] = { 3571, 16004, 26386, 16004, 3571 };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+motion_blur_kernel(BvBatch batch, BvPlane src, int bpc, int w, int h, uint16_t *__restrict__ blur,
+                   size_t blur_frame_elems)
+{
+    __shared__ uint16_t s_in[MB_TH + 2 * MB_R][MB_TW + 2 * MB_R];
+    __shared__ uint16_t s_v[MB_TH][MB_TW + 2 * MB_R];
+
+    const int f = blockIdx.z;
+    const uint8_t *img = src.p[f];
+    const int x0 = blockIdx.x * MB_TW, y0 = blockIdx.y * MB_TH;
+    const int tid = threadIdx.x;
+
+    for (int idx = tid; idx < (MB_TH + 2 * MB_R) * (MB_TW + 2 * MB_R); idx += 256) {
+        const int r = idx / (MB_TW + 2 * MB_R), c = idx - r * (MB_TW + 2 * MB_R);
+        const int gy = bv_mirror(min(y0 + r - MB_R, h + MB_R - 1), h);
+        const int gx = bv_mirror(min(x0 + c - MB_R, w + MB_R - 1), w);
+        s_in[r][c] = (uint16_t)bv_ld<T>(img, src.pitch, gy, gx);
+    }
+    __syncthreads();
+
+    const unsigned add_v = 1u << (bpc - 1);
+    for (int idx = tid; idx < MB_TH * (MB_TW + 2 * MB_R); idx += 256) {
+        const int r = idx / (MB_TW + 2 * MB_R), c = idx - r * (MB_TW + 2 * MB_R);
+        unsigned acc = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc += c_motion_filter[k] * (unsigned)s_in[r + k][c];
+        s_v[r][c] = (uint16_t)((acc + add_v) >> bpc);
+    }
+    __syncthreads();
+
+    uint16_t *out = blur + (size_t)f * blur_frame_elems;
+    for (int idx = tid; idx < MB_TH * MB_TW; idx += 256) {
+        const int r = idx / MB_TW, c = idx - r * MB_TW;
+        const int gy = y0 + r, gx = x0 + c;
+        if (gy < h && gx < w) {
+            unsigned acc = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) acc += c_motion_filter[k] * (unsigned)s_v[r][c + k];
+            out[(size_t)gy * w + gx] = (uint16_t)((acc + 32768u) >> 16);
+        }
+    }
+}
+
+// SAD of consecutive blurred frames.  Frame 0 of the group pairs with the last frame of the
+// previous group (prev_last); frames flagged BV_FRAME_FIRST have no predecessor (sad = 0).
+__global__ void __launch_bounds__(256)
+motion_sad_kernel(BvBatch batch, const uint16_t *__restrict__ blur, const uint16_t *__restrict__ prev_last,
+                  size_t frame_elems, size_t n_elems, unsigned long long *raw)
+{
+    __shared__ long long scratch[32];
+    const int f = blockIdx.y;
+    if (batch.flags[f] & BV_FRAME_FIRST) return;
+    const uint16_t *cur = blur + (size_t)f * frame_elems;
+    const uint16_t *prv = f == 0 ? prev_last : blur + (size_t)(f - 1) * frame_elems;
+    unsigned long long sad = 0;
+    const size_t n8 = n_elems / 8;
+    const uint4 *c4 = reinterpret_cast<const uint4 *>(cur);
+    const uint4 *p4 = reinterpret_cast<const uint4 *>(prv);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 a = __ldg(c4 + i), b = __ldg(p4 + i);
+        unsigned s = 0;
+        // per-halfword absolute differences, summed (max 8 * 65535 fits easily)
+        s += __vsadu2(a.x, b.x);
+        s += __vsadu2(a.y, b.y);
+        s += __vsadu2(a.z, b.z);
+        s += __vsadu2(a.w, b.w);
+        sad += s;
+    }
+    if (blockIdx.x == 0) {
+        for (size_t i = n8 * 8 + threadIdx.x; i < n_elems; i += blockDim.x)
+            sad += (unsigned)abs((int)cur[i] - (int)prv[i]);
+    }
+    long long v[1] = { (long long)sad };
+    bv_block_accumulate<1>(v, scratch, raw + (size_t)f * BV_RAW_WORDS + BV_RAW_SAD);
+}
+
+}  // namespace
+
+void bv_launch_motion_blur(const BvBatch &b, BvPlane ref_y, int bpc, int w, int h, uint16_t *blur_cur,
+                           size_t blur_frame_elems, cudaStream_t st, long long *nlaunch)
+{
+    dim3 grid((w + MB_TW - 1) / MB_TW, (h + MB_TH - 1) / MB_TH, b.n);
+    if (bpc == 8)
+        motion_blur_kernel<uint8_t><<<grid, 256, 0, st>>>(b, ref_y, bpc, w, h, blur_cur, blur_frame_elems);
+    else
+        motion_blur_kernel<uint16_t><<<grid, 256, 0, st>>>(b, ref_y, bpc, w, h, blur_cur, blur_frame_elems);
+    ++*nlaunch;
+}
+
+void bv_launch_motion_sad(const BvBatch &b, const uint16_t *blur_cur, const uint16_t *blur_prev_group_last,
+                          size_t blur_frame_elems, int w, int h, unsigned long long *raw, cudaStream_t st,
+                          long long *nlaunch)
+{
+    const size_t n = (size_t)w * h;
+    int gx = (int)((n / 8 + 255) / 256);
+    if (gx > 148 * 2) gx = 148 * 2;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, b.n);
+    motion_sad_kernel<<<grid, 256, 0, st>>>(b, blur_cur, blur_prev_group_last, blur_frame_elems, n, raw);
+    ++*nlaunch;
+}

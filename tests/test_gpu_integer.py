@@ -1,0 +1,154 @@
+"""GPU parity (bit-exact) of the integer extractors against the CPU oracle, through the C ABI.
+
+Every comparison is on the raw integer accumulators the kernels produce AND on the derived doubles
+(libvmaf's `integer_*` metrics).  The oracle (oracle/vmaf_oracle.c) restates libvmaf's
+integer_motion.c / integer_vif.c / integer_adm.c / integer_psnr.c."""
+import numpy as np
+import pytest
+
+import oracle
+from pqa2_b200 import _lib as L
+from pqa2_b200 import synth
+from pqa2_b200.extractor import FeatureExtractor
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_rows(frames, w, h, bpc, vif_egl=100.0, adm_egl=100.0):
+    rows = []
+    prev_blur = None
+    for (rp, dp) in frames:
+        blur = oracle.motion_blur(rp[0], bpc)
+        sad = 0 if prev_blur is None else oracle.motion_sad(blur, prev_blur)
+        prev_blur = blur
+        v = oracle.vif(rp[0], dp[0], bpc, vif_egl)
+        a = oracle.adm(rp[0], dp[0], bpc, adm_egl)
+        rows.append(dict(sad=sad, motion=oracle.motion_score(sad, w, h), vif=v, adm=a,
+                         sse=[oracle.sse(rp[k], dp[k], bpc) for k in range(len(rp))]))
+    return rows
+
+
+def _check(feat, row, w, h, bpc, planes=3):
+    raw = np.array(feat.raw[:], dtype=np.int64)
+    assert raw[L.RAW_SAD] == row["sad"]
+    assert feat.motion == row["motion"]
+    acc = raw[L.RAW_VIF:L.RAW_VIF + 28].reshape(4, 7)
+    np.testing.assert_array_equal(acc, row["vif"]["acc"])
+    for s in range(4):
+        assert feat.vif_num[s] == row["vif"]["num"][s]
+        assert feat.vif_den[s] == row["vif"]["den"][s]
+        assert feat.vif_scale[s] == row["vif"]["score"][s]
+    cm = raw[L.RAW_ADM_CM:L.RAW_ADM_CM + 12].reshape(4, 3)
+    dn = raw[L.RAW_ADM_DEN:L.RAW_ADM_DEN + 12].reshape(4, 3)
+    np.testing.assert_array_equal(cm, row["adm"]["cm"])
+    np.testing.assert_array_equal(dn.astype(np.uint64), row["adm"]["den"])
+    for s in range(4):
+        assert feat.adm_num[s] == row["adm"]["num_scale"][s]
+        assert feat.adm_den[s] == row["adm"]["den_scale"][s]
+    assert feat.adm2 == row["adm"]["adm2"]
+    for k in range(planes):
+        assert raw[L.RAW_SSE + k] == row["sse"][k]
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    assert feat.psnr_y == oracle.psnr_from_sse(row["sse"][0], bpc, w, h)
+    if planes == 3:
+        assert feat.psnr_cb == oracle.psnr_from_sse(row["sse"][1], bpc, cw, ch)
+        assert feat.psnr_cr == oracle.psnr_from_sse(row["sse"][2], bpc, cw, ch)
+
+
+FEATS = L.FEAT_VMAF_INT | L.FEAT_PSNR_Y | L.FEAT_PSNR_UV
+
+
+@pytest.mark.parametrize("w,h,bpc,nframes,batch", [
+    (176, 144, 8, 3, 0),
+    (322, 242, 8, 2, 0),        # odd-ish dims: VIF floors, ADM ceils
+    (333, 251, 8, 2, 0),        # odd dims, unaligned rows
+    (640, 360, 8, 6, 4),        # group boundary inside the clip (motion state carried over)
+    (416, 240, 10, 3, 2),
+    (1920, 1080, 8, 1, 0),
+    (960, 540, 10, 1, 0),
+    (48, 36, 8, 2, 0),          # smaller than one tile
+])
+def test_integer_features_bit_exact(w, h, bpc, nframes, batch):
+    frames = [synth.frame_pair(3, f, w, h, bpc) for f in range(nframes)]
+    rows = _oracle_rows(frames, w, h, bpc)
+    with FeatureExtractor(w, h, bpc, 420, FEATS, batch_frames=batch) as fx:
+        for f, (rp, dp) in enumerate(frames):
+            fx.submit(f, rp, dp, L.FRAME_FIRST if f == 0 else 0)
+        fx.flush()
+        out = fx.fetch()
+        assert fx.kernel_launches > 0
+    for f in range(nframes):
+        assert out[f].frame_index == f
+        _check(out[f], rows[f], w, h, bpc)
+
+
+def test_neg_gain_limits():
+    """vmaf_*neg models: both enhancement gain limits = 1.0 (reference models/vmaf_v0.6.1neg.json:34-51)."""
+    w, h = 480, 270
+    frames = [synth.frame_pair(5, f, w, h, 8) for f in range(2)]
+    rows = _oracle_rows(frames, w, h, 8, vif_egl=1.0, adm_egl=1.0)
+    rows_default = _oracle_rows(frames, w, h, 8)
+    assert not np.array_equal(rows[0]["vif"]["acc"], rows_default[0]["vif"]["acc"])   # the patch sharpens
+    assert not np.array_equal(rows[0]["adm"]["cm"], rows_default[0]["adm"]["cm"])
+    with FeatureExtractor(w, h, 8, 420, FEATS, vif_enhn_gain_limit=1.0, adm_enhn_gain_limit=1.0) as fx:
+        for f, (rp, dp) in enumerate(frames):
+            fx.submit(f, rp, dp, L.FRAME_FIRST if f == 0 else 0)
+        out = fx.fetch()
+    for f in range(2):
+        _check(out[f], rows[f], w, h, 8)
+
+
+def test_identical_pair_and_static_clip():
+    """SURVEY.md §8c pins: identical ref/dis => vif ~ 1, adm2 ~ 1, psnr_y = 60; static clip => motion = 0."""
+    w, h = 352, 288
+    rp, _ = synth.frame_pair(1, 0, w, h, 8)
+    with FeatureExtractor(w, h, 8, 420, FEATS) as fx:
+        for f in range(3):
+            fx.submit(f, rp, rp, L.FRAME_FIRST if f == 0 else 0)
+        out = fx.fetch()
+    for f in range(3):
+        assert out[f].motion == 0.0
+        assert out[f].psnr_y == 60.0
+        for s in range(4):
+            assert abs(out[f].vif_scale[s] - 1.0) < 1e-4
+        assert abs(out[f].adm2 - 1.0) < 1e-4
+
+
+def test_lead_in_and_subsample_flags():
+    """Frame shards: a lead-in frame only feeds the motion state; n_subsample skips VIF/ADM."""
+    w, h = 320, 180
+    frames = [synth.frame_pair(9, f, w, h, 8) for f in range(5)]
+    rows = _oracle_rows(frames, w, h, 8)
+    # shard [2, 5) with frame 1 as lead-in; frame 3 skipped spatially
+    with FeatureExtractor(w, h, 8, 420, FEATS, batch_frames=3) as fx:
+        fx.submit(1, *frames[1], L.FRAME_LEAD_IN | L.FRAME_FIRST)
+        fx.submit(2, *frames[2], 0)
+        fx.submit(3, *frames[3], L.FRAME_SKIP_SPATIAL)
+        fx.submit(4, *frames[4], 0)
+        out = fx.fetch()
+    assert out[0].valid_mask == 0
+    _check(out[1], rows[2], w, h, 8)
+    assert out[2].valid_mask == L.FEAT_MOTION and out[2].motion == rows[3]["motion"]
+    _check(out[3], rows[4], w, h, 8)
+
+
+def test_device_resident_submission_matches_host_submission():
+    from pqa2_b200.extractor import DeviceBuffer
+    w, h = 640, 360
+    frames = [synth.frame_pair(2, f, w, h, 8, chroma=False) for f in range(3)]
+    with FeatureExtractor(w, h, 8, 0, L.FEAT_VMAF_INT | L.FEAT_PSNR_Y) as fx:
+        for f, (rp, dp) in enumerate(frames):
+            fx.submit(f, rp, dp, L.FRAME_FIRST if f == 0 else 0)
+        host = fx.fetch()
+    buf = DeviceBuffer(w * h * 2 * 3)
+    for f, (rp, dp) in enumerate(frames):
+        buf.upload((2 * f) * w * h, rp[0])
+        buf.upload((2 * f + 1) * w * h, dp[0])
+    with FeatureExtractor(w, h, 8, 0, L.FEAT_VMAF_INT | L.FEAT_PSNR_Y) as fx:
+        for f in range(3):
+            fx.submit_device(f, [(buf.ptr + (2 * f) * w * h, w)], [(buf.ptr + (2 * f + 1) * w * h, w)],
+                             L.FRAME_FIRST if f == 0 else 0)
+        dev = fx.fetch()
+    for f in range(3):
+        assert list(host[f].raw) == list(dev[f].raw)
+    buf.free()
