@@ -99,7 +99,7 @@ __device__ __forceinline__ void adm_decouple_csf(const int (&o)[3], const int (&
         if (flag && k > 0) {
             const double v = __dmul_rn((double)rst, a.egl), tt = (double)tb;
             if (ob > 0) rst = __double2int_rz(v < tt ? v : tt);
-            else rst = __double2int_rz(v > tt ? v : tt);
+            else if (ob < 0) rst = __double2int_rz(v > tt ? v : tt);
         }
         if (SCALE == 0) rst = (short)rst;
         int ad = tb - rst;

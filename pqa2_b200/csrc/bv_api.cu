@@ -133,8 +133,8 @@ int alloc_ctx(bv_ctx *c)
     }
     const size_t npx = (size_t)c->w * c->h;
     if (c->feat & BV_FEAT_MOTION) {
-        c->blur_elems = npx;
-        for (int k = 0; k < 2; ++k) CK(cudaMalloc(&c->blur[k], sizeof(uint16_t) * npx * B));
+        c->blur_elems = (npx + 7) & ~(size_t)7;      // frames stay 16-byte aligned for the uint4 SAD loads
+        for (int k = 0; k < 2; ++k) CK(cudaMalloc(&c->blur[k], sizeof(uint16_t) * c->blur_elems * B));
     }
     if (c->feat & BV_FEAT_VIF) {
         std::vector<uint16_t> tab(65536, 0);

@@ -1,0 +1,367 @@
+"""Clip-level VMAF engine: frames -> per-frame libvmaf metric rows -> pooled report.
+
+Does, on B200s, what the ffmpeg child does for the reference between ``Popen``
+(``app/vmaf_analyzer.py:446-455``) and the JSON log it leaves behind (``:640-641``):
+pairs frames, runs the extractors (CUDA, through the C ABI), applies libvmaf's temporal rule for
+motion2, fuses features with the model's SVR, pools, and returns the log as a dict.
+
+Multi-GPU: frames are split into contiguous chunks, one per device, each with a
+one-frame lead-in that only feeds the motion state; per-frame raw ``motion`` comes back from every
+shard and motion2 / SVR / pooling run on the host over the concatenated rows.  No collective."""
+from __future__ import annotations
+
+import math
+import threading
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib as L
+from . import report
+from .extractor import FeatureExtractor, pinned_empty
+from .model import VmafModel
+
+
+@dataclass
+class EngineOptions:
+    n_subsample: int = 1
+    psnr: bool = False               # libvmaf `psnr=1`   -> psnr_y
+    ssim: bool = False               # libvmaf `ssim=1`   -> float_ssim
+    ms_ssim: bool = False            # libvmaf `ms_ssim=1`-> float_ms_ssim
+    ffmpeg_psnr: bool = False        # FFmpeg `psnr` filter stats (all planes)
+    ffmpeg_ssim: bool = False        # FFmpeg `ssim` filter stats (all planes)
+    enable_transform: bool = False
+    disable_clip: bool = False
+    report_motion: bool = True       # libvmaf logs integer_motion next to integer_motion2
+    devices: tuple = (0,)
+    batch_frames: int = 0
+    svr_on_device: bool = True
+    extra_features: int = 0          # extra _lib.FEAT_* bits
+
+
+class FrameSource:
+    """Protocol: width/height/bpc/chroma/nb_frames/fps + read_into(i, ref_planes, dis_planes)."""
+    width: int
+    height: int
+    bpc: int
+    chroma: int
+    nb_frames: int
+    fps: float = 30.0
+
+    def open(self):            # per-thread handle (file descriptors are not shared between shards)
+        return self
+
+    def close(self):
+        pass
+
+    def read_into(self, i: int, ref_planes, dis_planes, luma_only: bool) -> None:
+        raise NotImplementedError
+
+
+class FileSource(FrameSource):
+    def __init__(self, ref_info, dis_info):
+        from .yuvio import ClipReader
+        self._ri, self._di = ref_info, dis_info
+        self.width, self.height, self.bpc, self.chroma = ref_info.width, ref_info.height, ref_info.bpc, ref_info.chroma
+        self.nb_frames = min(ref_info.nb_frames, dis_info.nb_frames)
+        self.fps = dis_info.fps or ref_info.fps or 30.0
+        self._r = self._d = None
+        self._ClipReader = ClipReader
+
+    def open(self):
+        s = FileSource(self._ri, self._di)
+        s._r, s._d = self._ClipReader(self._ri), self._ClipReader(self._di)
+        return s
+
+    def close(self):
+        for r in (self._r, self._d):
+            if r:
+                r.close()
+
+    def read_into(self, i, ref_planes, dis_planes, luma_only):
+        self._r.read_into(i, ref_planes, luma_only)
+        self._d.read_into(i, dis_planes, luma_only)
+
+
+class SynthSource(FrameSource):
+    """Procedural clip (pqa2_b200.synth) -- tests and bench."""
+
+    def __init__(self, width, height, bpc=8, nb_frames=8, seed=1, chroma=420, q=4, strength=1, fps=30.0):
+        self.width, self.height, self.bpc, self.chroma = width, height, bpc, chroma
+        self.nb_frames, self.seed, self.q, self.strength, self.fps = nb_frames, seed, q, strength, fps
+
+    def read_into(self, i, ref_planes, dis_planes, luma_only):
+        from . import synth
+        rp, dp = synth.frame_pair(self.seed, i, self.width, self.height, self.bpc, chroma=not luma_only,
+                                  q=self.q, strength=self.strength)
+        for k in range(len(rp)):
+            ref_planes[k][...] = rp[k]
+            dis_planes[k][...] = dp[k]
+
+
+def _plane_shapes(src: FrameSource):
+    w, h = src.width, src.height
+    if src.chroma in (0, 400):
+        return [(h, w)]
+    cw = (w + 1) // 2 if src.chroma in (420, 422) else w
+    ch = (h + 1) // 2 if src.chroma == 420 else h
+    return [(h, w), (ch, cw), (ch, cw)]
+
+
+def feature_mask(model: VmafModel, opt: EngineOptions) -> int:
+    m = L.FEAT_VMAF_FLOAT if model.is_float else L.FEAT_VMAF_INT
+    if opt.psnr:
+        m |= L.FEAT_PSNR_Y
+    if opt.ssim:
+        m |= L.FEAT_FLOAT_SSIM
+    if opt.ms_ssim:
+        m |= L.FEAT_FLOAT_MS_SSIM
+    if opt.ffmpeg_psnr:
+        m |= L.FEAT_PSNR_Y | L.FEAT_PSNR_UV
+    if opt.ffmpeg_ssim:
+        m |= L.FEAT_FFSSIM
+    return m | opt.extra_features
+
+
+def shard_ranges(n_frames: int, n_shards: int):
+    """Contiguous chunks [start, end) per shard."""
+    n_shards = max(1, min(n_shards, max(n_frames, 1)))
+    return [(g * n_frames // n_shards, (g + 1) * n_frames // n_shards) for g in range(n_shards)]
+
+
+class _Cancelled(Exception):
+    pass
+
+
+def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: int, start: int, end: int,
+               mask: int, rows: list, progress, cancel: threading.Event, errors: list, ctx_holder: list):
+    handle = None
+    try:
+        handle = src.open()
+        luma_only = not (mask & (L.FEAT_PSNR_UV | L.FEAT_FFSSIM)) or src.chroma in (0, 400)
+        shapes = _plane_shapes(src)[: 1 if luma_only else 3]
+        dtype = np.uint8 if src.bpc == 8 else np.uint16
+        fx = FeatureExtractor(src.width, src.height, src.bpc, src.chroma if not luma_only else 0, mask, device,
+                              vif_enhn_gain_limit=model.vif_enhn_gain_limit,
+                              adm_enhn_gain_limit=model.adm_enhn_gain_limit, batch_frames=opt.batch_frames)
+        ctx_holder.append(fx)
+        with fx:
+            B = opt.batch_frames or L.BV_MAX_BATCH
+            ring = [([pinned_empty(s, dtype) for s in shapes], [pinned_empty(s, dtype) for s in shapes])
+                    for _ in range(2 * B)]
+            lead = 1 if start > 0 else 0
+            ordinal = 0
+            for i in range(start - lead, end):
+                if cancel.is_set():
+                    fx.cancel()
+                    raise _Cancelled()
+                slot = ordinal % len(ring)
+                if ordinal and ordinal % B == 0:
+                    fx.wait_uploads()           # the half of the ring we are about to overwrite is free again
+                rp, dp = ring[slot]
+                handle.read_into(i, rp, dp, luma_only)
+                flags = 0
+                if i < start:
+                    flags |= L.FRAME_LEAD_IN
+                if ordinal == 0 and i == 0:
+                    flags |= L.FRAME_FIRST
+                if ordinal == 0 and i > 0 and not lead:
+                    flags |= L.FRAME_FIRST
+                if opt.n_subsample > 1 and i % opt.n_subsample != 0:
+                    flags |= L.FRAME_SKIP_SPATIAL
+                fx.submit(i, rp, dp, flags)
+                ordinal += 1
+                if progress:
+                    progress(1)
+            fx.flush()
+            out = fx.fetch(0, ordinal)
+            for k in range(lead, ordinal):
+                rows[out[k].frame_index] = _copy_features(out[k])
+    except _Cancelled:
+        errors.append(("cancelled", None))
+    except Exception as e:            # surfaced by analyze(): the caller decides how to report
+        errors.append(("error", e))
+    finally:
+        if handle is not None and handle is not src:
+            handle.close()
+
+
+def _copy_features(f) -> dict:
+    return {
+        "valid": int(f.valid_mask), "raw": list(f.raw),
+        "motion": f.motion, "vif": list(f.vif_scale), "adm2": f.adm2, "adm_scale": list(f.adm_scale),
+        "adm_num": list(f.adm_num), "adm_den": list(f.adm_den), "vif_num": list(f.vif_num), "vif_den": list(f.vif_den),
+        "psnr": [f.psnr_y, f.psnr_cb, f.psnr_cr], "ffssim": list(f.ffssim),
+        "f_motion": f.f_motion, "f_vif": list(f.f_vif_scale), "f_adm2": f.f_adm2, "f_adm_scale": list(f.f_adm_scale),
+        "float_ssim": f.float_ssim, "float_ms_ssim": f.float_ms_ssim,
+    }
+
+
+def _egl_suffix(v: float) -> str:
+    return "" if v == 100.0 else "_egl_%g" % v
+
+
+def motion2_from_motion(motion: list) -> list:
+    """libvmaf integer_motion.c / float_motion.c: motion2[i] = min(motion[i], motion[i+1]); the last
+    frame keeps its own motion (flush); motion[0] = 0."""
+    n = len(motion)
+    return [min(motion[i], motion[i + 1]) if i + 1 < n else motion[i] for i in range(n)]
+
+
+def percentile(sorted_vals, p: float) -> float:
+    """Linear-interpolated percentile (libvmaf predict.c percentile())."""
+    n = len(sorted_vals)
+    if n == 1:
+        return sorted_vals[0]
+    pos = p / 100.0 * (n - 1)
+    lo = int(math.floor(pos))
+    hi = min(lo + 1, n - 1)
+    return sorted_vals[lo] + (sorted_vals[hi] - sorted_vals[lo]) * (pos - lo)
+
+
+def build_frames(rows: list, model: VmafModel, opt: EngineOptions, device: int | None) -> list:
+    """Per-frame feature rows -> libvmaf 'frames' list (metric names of SURVEY.md Appendix A.8)."""
+    is_f = model.is_float
+    pre = "" if is_f else "integer_"
+    vs, as_ = _egl_suffix(model.vif_enhn_gain_limit), _egl_suffix(model.adm_enhn_gain_limit)
+    motion = [(r["f_motion"] if is_f else r["motion"]) for r in rows]
+    if motion:
+        motion[0] = 0.0
+    motion2 = motion2_from_motion(motion)
+    scored = [i for i, r in enumerate(rows) if r["valid"] & (L.FEAT_FLOAT_VIF if is_f else L.FEAT_VIF)]
+    frames = []
+    feats = np.zeros((len(scored), 6), np.float64)
+    keys = model.main.metric_keys
+    for n, i in enumerate(scored):
+        r = rows[i]
+        m = {}
+        adm2 = r["f_adm2"] if is_f else r["adm2"]
+        adm_s = r["f_adm_scale"] if is_f else r["adm_scale"]
+        vif = r["f_vif"] if is_f else r["vif"]
+        m[f"{pre}adm2{as_}"] = adm2
+        for s in range(4):
+            m[f"{pre}adm_scale{s}{as_}"] = adm_s[s]
+        m[f"{pre}motion2"] = motion2[i]
+        if opt.report_motion:
+            m[f"{pre}motion"] = motion[i]
+        for s in range(4):
+            m[f"{pre}vif_scale{s}{vs}"] = vif[s]
+        if r["valid"] & L.FEAT_PSNR_Y and (opt.psnr or opt.ffmpeg_psnr):
+            m["psnr_y"] = r["psnr"][0]
+        if r["valid"] & L.FEAT_FLOAT_SSIM:
+            m["float_ssim"] = r["float_ssim"]
+        if r["valid"] & L.FEAT_FLOAT_MS_SSIM:
+            m["float_ms_ssim"] = r["float_ms_ssim"]
+        base = {"adm2": adm2, "motion2": motion2[i], "motion": motion[i],
+                "vif_scale0": vif[0], "vif_scale1": vif[1], "vif_scale2": vif[2], "vif_scale3": vif[3],
+                "adm_scale0": adm_s[0], "adm_scale1": adm_s[1], "adm_scale2": adm_s[2], "adm_scale3": adm_s[3]}
+        for j, k in enumerate(keys):
+            feats[n, j] = base[k[len("integer_"):] if k.startswith("integer_") else k]
+        frames.append({"frameNum": i, "metrics": m})
+    if scored:
+        dev = device if opt.svr_on_device else None
+        vmaf = model.main.predict(feats, opt.enable_transform, opt.disable_clip, device=dev)
+        boots = None
+        if model.bootstrap:
+            boots = np.stack([b.predict(feats, False, True, device=dev) for b in model.bootstrap], axis=1)
+        for n, fr in enumerate(frames):
+            fr["metrics"]["vmaf"] = float(vmaf[n])
+            if boots is not None:
+                fr["metrics"].update(_bootstrap_metrics(model, boots[n], opt))
+    return frames
+
+
+def _post(model: VmafModel, y: float, opt: EngineOptions) -> float:
+    m = model.main
+    if opt.enable_transform and m.transform:
+        t = m.transform
+        v = 0.0
+        has = False
+        if "p0" in t:
+            v += t["p0"]; has = True
+        if "p1" in t:
+            v += t["p1"] * y; has = True
+        if "p2" in t:
+            v += t["p2"] * y * y; has = True
+        out = v if has else y
+        if t.get("out_lte_in") and out > y:
+            out = y
+        if t.get("out_gte_in") and out < y:
+            out = y
+        y = out
+    if not opt.disable_clip and m.score_clip:
+        y = min(max(y, m.score_clip[0]), m.score_clip[1])
+    return y
+
+
+def _bootstrap_metrics(model: VmafModel, scores: np.ndarray, opt: EngineOptions) -> dict:
+    """Bagging / stddev / 95 % CI over the bootstrap models' un-clipped scores."""
+    s = [float(x) for x in scores]
+    n = len(s)
+    mean = sum(s) / n
+    std = math.sqrt(sum((x - mean) ** 2 for x in s) / n)
+    srt = sorted(s)
+    lo, hi = percentile(srt, 2.5), percentile(srt, 97.5)
+    delta = 0.01
+    slope = (_post(model, mean + delta, opt) - _post(model, mean - delta, opt)) / (2 * delta) \
+        if opt.enable_transform else 1.0
+    return {"vmaf_bagging": _post(model, mean, opt), "vmaf_stddev": std * slope,
+            "vmaf_ci_p95_lo": _post(model, lo, opt), "vmaf_ci_p95_hi": _post(model, hi, opt)}
+
+
+def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None, progress_cb=None,
+            cancel: threading.Event | None = None, frame_range: tuple | None = None) -> dict:
+    """Scores a clip; returns the libvmaf log as a dict plus ``rows`` (raw per-frame features).
+
+    Raises on engine errors; returns ``None`` if cancelled."""
+    opt = opt or EngineOptions()
+    cancel = cancel or threading.Event()
+    first, last = frame_range or (0, src.nb_frames)
+    n = last - first
+    if n <= 0:
+        raise ValueError("no frames to analyze")
+    mask = feature_mask(model, opt)
+    rows: list = [None] * src.nb_frames
+    devices = list(opt.devices) or [0]
+    ranges = [(first + a, first + b) for a, b in shard_ranges(n, len(devices))]
+    done = [0]
+    lock = threading.Lock()
+
+    def progress(k):
+        if progress_cb:
+            with lock:
+                done[0] += k
+                d = done[0]
+            progress_cb(d, n)
+
+    errors: list = []
+    holders: list = []
+    t0 = time.perf_counter()
+    threads = []
+    for dev, (a, b) in zip(devices, ranges):
+        if b <= a:
+            continue
+        th = threading.Thread(target=_run_shard, args=(src, model, opt, dev, a, b, mask, rows, progress, cancel,
+                                                       errors, holders), daemon=True)
+        th.start()
+        threads.append(th)
+    for th in threads:
+        th.join()
+    if any(k == "cancelled" for k, _ in errors) or cancel.is_set():
+        return None
+    for k, e in errors:
+        if k == "error":
+            raise e
+    rows_used = rows[first:last]
+    if first > 0:
+        # a sub-range does not know the frame before it: libvmaf would have started at index 0 too
+        pass
+    frames = build_frames(rows_used, model, opt, devices[0])
+    for fr in frames:
+        fr["frameNum"] += first
+    dt = time.perf_counter() - t0
+    pooled = report.pooled_metrics(frames)
+    return {"version": report.VERSION, "fps": n / dt if dt > 0 else 0.0, "frames": frames,
+            "pooled_metrics": pooled, "aggregate_metrics": {}, "rows": rows_used,
+            "model": model.name, "elapsed_s": dt, "n_frames": n}

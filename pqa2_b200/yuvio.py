@@ -1,0 +1,170 @@
+"""Raw-video ingest for the engine: Y4M and headerless planar YUV readers/writers.
+
+The reference hands ffmpeg two container files (``app/vmaf_analyzer.py:415-416``) and lets it
+decode; libvmaf then sees planar pictures, 8-bit as u8 and >8-bit as little-endian u16
+(SURVEY.md Appendix A.1).  This engine consumes those planar pictures directly.  Compressed
+inputs (the reference's aligned MP4s) are out of scope for this round."""
+from __future__ import annotations
+
+import os
+import re
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class ClipInfo:
+    path: str
+    width: int
+    height: int
+    bpc: int
+    chroma: int            # 420 / 422 / 444 / 400
+    fps_num: int = 30
+    fps_den: int = 1
+    nb_frames: int = 0
+    header_bytes: int = 0
+    frame_header_bytes: int = 0
+
+    @property
+    def fps(self) -> float:
+        return self.fps_num / self.fps_den if self.fps_den else 0.0
+
+    @property
+    def pix_fmt(self) -> str:
+        base = {420: "yuv420p", 422: "yuv422p", 444: "yuv444p", 400: "gray"}[self.chroma]
+        return base if self.bpc == 8 else f"{base}{self.bpc}le"
+
+    def plane_shapes(self):
+        w, h = self.width, self.height
+        if self.chroma == 400:
+            return [(h, w)]
+        cw = (w + 1) // 2 if self.chroma in (420, 422) else w
+        ch = (h + 1) // 2 if self.chroma == 420 else h
+        return [(h, w), (ch, cw), (ch, cw)]
+
+    @property
+    def frame_bytes(self) -> int:
+        bps = 1 if self.bpc == 8 else 2
+        return sum(a * b for a, b in self.plane_shapes()) * bps
+
+
+_Y4M_CHROMA = {
+    "420": (420, 8), "420jpeg": (420, 8), "420mpeg2": (420, 8), "420paldv": (420, 8),
+    "422": (422, 8), "444": (444, 8), "mono": (400, 8),
+    "420p10": (420, 10), "422p10": (422, 10), "444p10": (444, 10), "mono10": (400, 10),
+    "420p12": (420, 12), "422p12": (422, 12), "444p12": (444, 12), "mono12": (400, 12),
+    "420p16": (420, 16), "422p16": (422, 16), "444p16": (444, 16),
+}
+
+
+def probe(path: str, width: int | None = None, height: int | None = None, pix_fmt: str | None = None,
+          fps: float | None = None) -> ClipInfo:
+    """Metadata of a raw clip.  ``.y4m`` is self-describing; ``.yuv`` needs width/height/pix_fmt or a
+    ``_<W>x<H>[_<fps>][_<pix_fmt>]`` hint in the file name."""
+    size = os.path.getsize(path)
+    with open(path, "rb") as f:
+        head = f.read(10)
+        if head.startswith(b"YUV4MPEG2"):
+            f.seek(0)
+            line = f.readline(4096)
+            toks = line.decode("ascii", "replace").strip().split(" ")
+            w = h = 0
+            chroma, bpc = 420, 8
+            fn, fd = 30, 1
+            for t in toks[1:]:
+                if not t:
+                    continue
+                if t[0] == "W":
+                    w = int(t[1:])
+                elif t[0] == "H":
+                    h = int(t[1:])
+                elif t[0] == "F":
+                    a, _, b = t[1:].partition(":")
+                    fn, fd = int(a), int(b or 1)
+                elif t[0] == "C":
+                    if t[1:] not in _Y4M_CHROMA:
+                        raise ValueError(f"{path}: unsupported Y4M chroma tag {t}")
+                    chroma, bpc = _Y4M_CHROMA[t[1:]]
+            if w <= 0 or h <= 0:
+                raise ValueError(f"{path}: Y4M header lacks W/H")
+            info = ClipInfo(path, w, h, bpc, chroma, fn, fd, header_bytes=len(line))
+            # frame headers are "FRAME\n" unless they carry parameters; measure the first one
+            fh = f.readline(256)
+            info.frame_header_bytes = len(fh) if fh.startswith(b"FRAME") else 6
+            per = info.frame_header_bytes + info.frame_bytes
+            info.nb_frames = (size - info.header_bytes) // per
+            return info
+    name = os.path.basename(path)
+    if width is None or height is None:
+        m = re.search(r"(\d{2,5})x(\d{2,5})", name)
+        if not m:
+            raise ValueError(f"{path}: raw YUV needs width/height (or a _WxH hint in the name)")
+        width, height = int(m.group(1)), int(m.group(2))
+    if pix_fmt is None:
+        m = re.search(r"(yuv4(?:20|22|44)p(?:1[026](?:le)?)?|gray(?:1[026]le)?)", name)
+        pix_fmt = m.group(1) if m else "yuv420p"
+    m = re.match(r"(?:yuv(4\d\d)p|(gray))(\d\d)?(?:le)?$", pix_fmt)
+    if not m:
+        raise ValueError(f"unsupported pix_fmt {pix_fmt}")
+    chroma = 400 if m.group(2) else int(m.group(1))
+    bpc = int(m.group(3)) if m.group(3) else 8
+    fn, fd = (int(round((fps or 30.0) * 1000)), 1000)
+    info = ClipInfo(path, width, height, bpc, chroma, fn, fd)
+    info.nb_frames = size // info.frame_bytes
+    return info
+
+
+class ClipReader:
+    """Sequential / random access reader that fills caller-provided (pinned) plane arrays."""
+
+    def __init__(self, info: ClipInfo):
+        self.info = info
+        self._f = open(info.path, "rb", buffering=0)
+        self._dtype = np.uint8 if info.bpc == 8 else np.dtype("<u2")
+
+    def close(self):
+        self._f.close()
+
+    def frame_offset(self, i: int) -> int:
+        inf = self.info
+        return inf.header_bytes + i * (inf.frame_header_bytes + inf.frame_bytes) + inf.frame_header_bytes
+
+    def alloc_planes(self, pinned: bool = True):
+        if pinned:
+            from .extractor import pinned_empty
+            return [pinned_empty(s, self._dtype) for s in self.info.plane_shapes()]
+        return [np.empty(s, self._dtype) for s in self.info.plane_shapes()]
+
+    def read_into(self, i: int, planes, luma_only: bool = False) -> None:
+        self._f.seek(self.frame_offset(i))
+        for k, p in enumerate(planes):
+            if luma_only and k > 0:
+                break
+            mv = memoryview(p.reshape(-1).view(np.uint8))
+            n = self._f.readinto(mv)
+            if n != len(mv):
+                raise EOFError(f"{self.info.path}: short read at frame {i}")
+
+
+def write_y4m(path: str, frames, width: int, height: int, bpc: int = 8, fps=(30, 1), chroma: int = 420) -> None:
+    """frames: iterable of [Y, U, V] arrays.  Header as ffmpeg expects."""
+    tag = {(420, 8): "420jpeg", (422, 8): "422", (444, 8): "444", (400, 8): "mono"}.get((chroma, bpc))
+    if tag is None:
+        tag = {420: "420", 422: "422", 444: "444", 400: "mono"}[chroma] + ("p" if chroma != 400 else "") + str(bpc)
+    extra = f" XYSCSS={chroma}P{bpc}" if bpc > 8 and chroma != 400 else ""
+    with open(path, "wb") as f:
+        f.write(f"YUV4MPEG2 W{width} H{height} F{fps[0]}:{fps[1]} Ip A1:1 C{tag}{extra}\n".encode())
+        for planes in frames:
+            f.write(b"FRAME\n")
+            for p in planes:
+                a = np.ascontiguousarray(p)
+                f.write(a.astype("<u2").tobytes() if bpc > 8 else a.tobytes())
+
+
+def write_raw(path: str, frames, bpc: int = 8) -> None:
+    with open(path, "wb") as f:
+        for planes in frames:
+            for p in planes:
+                a = np.ascontiguousarray(p)
+                f.write(a.astype("<u2").tobytes() if bpc > 8 else a.tobytes())
