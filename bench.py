@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py -- VMAF frames/sec on B200 (BASELINE.json metric), with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A *step* is one pass of the hot path over one batch of `frames_per_step` synthetic ref/dis frame
+pairs per GPU (weak scaling: frame chunks are independent, there is no data-path collective --
+SURVEY.md §8e).  `value` = frame pairs per second over all GPUs with the clips resident in HBM;
+`e2e` = the same through the public engine call (pqa2_b200.engine.analyze) from pinned HOST frames,
+host->device copies and the feature read-back inside the timed region.
+
+Workloads (BASELINE.json `configs`):
+  1080p-float  configs[1]: 1080p yuv420p 8-bit, vmaf_float_v0.6.1 + psnr + float_ssim + float_ms_ssim
+  1080p-int    configs[0] shape: 1080p 8-bit, vmaf_v0.6.1 (integer extractors)
+  4k-int       configs[2]: 2160p yuv420p10le, vmaf_4k_v0.6.1
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "1080p-float": dict(w=1920, h=1080, bpc=8, model="vmaf_float_v0.6.1", psnr=True, ssim=True, ms_ssim=True,
+                        frames_per_step=128, pool=64, cfg="configs[1]"),
+    "1080p-int": dict(w=1920, h=1080, bpc=8, model="vmaf_v0.6.1", psnr=False, ssim=False, ms_ssim=False,
+                      frames_per_step=256, pool=64, cfg="configs[0] shape"),
+    "4k-int": dict(w=3840, h=2160, bpc=10, model="vmaf_4k_v0.6.1", psnr=False, ssim=False, ms_ssim=False,
+                   frames_per_step=64, pool=24, cfg="configs[2]"),
+}
+
+# Algorithmic bytes per frame pair of each kernel at (w, h, bytes per sample): unique bytes the
+# kernel must read + must write (DESIGN.md "Kernels").
+def kernel_bytes(name: str, w: int, h: int, bps: int) -> float | None:
+    px = w * h
+    lv = [((w >> s) * (h >> s)) for s in range(4)]                       # VIF level pixel counts
+    ad = []
+    cw, ch = w, h
+    for _ in range(4):
+        cw, ch = (cw + 1) // 2, (ch + 1) // 2
+        ad.append(cw * ch)
+    t = {
+        "motion_blur": px * bps + px * 2,
+        "motion_sad": 2 * px * 2,
+        "vif_stat_s0": 2 * px * bps, "vif_subsample_s1": 2 * px * bps + 2 * lv[1] * 2,
+        "vif_stat_s1": 2 * lv[1] * 2, "vif_subsample_s2": 2 * lv[1] * 2 + 2 * lv[2] * 2,
+        "vif_stat_s2": 2 * lv[2] * 2, "vif_subsample_s3": 2 * lv[2] * 2 + 2 * lv[3] * 2,
+        "vif_stat_s3": 2 * lv[3] * 2,
+        "adm_scale0": 2 * px * bps + 2 * ad[0] * 2, "adm_scale1": 2 * ad[0] * 2 + 2 * ad[1] * 4,
+        "adm_scale2": 2 * ad[1] * 4 + 2 * ad[2] * 4, "adm_scale3": 2 * ad[2] * 4,
+        "psnr_sse_y": 2 * px * bps,
+    }
+    return t.get(name)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._pump, daemon=True)
+        self.t.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if p[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks() -> tuple:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle (CPU restatement of libvmaf's path; the reference's own
+# ffmpeg+libvmaf cannot run in this image -- SURVEY.md §8c) on the host cores.
+# --------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, f0, n, w, h, bpc, kind = args
+    import oracle
+    from pqa2_b200 import synth
+    frames = [synth.frame_pair(seed, f0 + i, w, h, bpc, chroma=False) for i in range(n + 1)]
+    t0 = time.perf_counter()
+    prev = oracle.motion_blur(frames[0][0][0], bpc)
+    for i in range(1, n + 1):
+        rp, dp = frames[i]
+        if kind == "float":
+            oracle.float_features(rp[0], dp[0], bpc, prev_ref=frames[i - 1][0][0], psnr=True, ssim=True, ms_ssim=True)
+        else:
+            blur = oracle.motion_blur(rp[0], bpc)
+            oracle.motion_sad(blur, prev)
+            prev = blur
+            oracle.vif(rp[0], dp[0], bpc)
+            oracle.adm(rp[0], dp[0], bpc)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl: dict, frames_per_core: int = 2) -> dict:
+    import multiprocessing as mp
+    import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    kind = "float" if "float" in wl["model"] else "int"
+    jobs = [(1, 10 * c, frames_per_core, wl["w"], wl["h"], wl["bpc"], kind) for c in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_cpu_worker, [(1, 0, 0, 64, 64, 8, kind)] * cores)           # start workers, load the oracle
+        t0 = time.perf_counter()
+        busy = pool.map(_cpu_worker, jobs)
+        dt = time.perf_counter() - t0
+    n = cores * frames_per_core
+    return {"value": n / max(busy), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{n} synthetic {wl['w']}x{wl['h']} {wl['bpc']}-bit frame pairs ({frames_per_core} per core), "
+                      f"oracle/ ({'float' if kind == 'float' else 'integer'} extractors, scalar C -O2); "
+                      f"wall {dt:.1f}s incl. frame synthesis"}
+
+
+def reference_arm(args, wl, wname):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    times = []
+    base = None
+    for s in range(args.warmup + args.steps):
+        base = cpu_baseline(wl, frames_per_core=1)
+        if s >= args.warmup:
+            times.append(base["value"])
+    v = statistics.mean(times) if times else 0.0
+    base["value"] = v
+    out = {"impl": "reference", "metric": "vmaf_frames_per_sec", "value": v, "unit": "frames/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1000.0 * (os.cpu_count() or 1) / v if v else None, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": wl_dtype(wl), "data": "synthetic",
+           "config": bench_config(wl, wname, 0, args.gpus),
+           "cpu_baseline": base, "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0,
+           "note": "CPU restatement of the libvmaf path (oracle/), all host cores; ffmpeg+libvmaf is not installable here"}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def wl_dtype(wl) -> str:
+    return "f32" if "float" in wl["model"] else "int32/int64 fixed-point"
+
+
+def bench_config(wl, wname, fps, n_gpus) -> dict:
+    return {"workload": f"{wname}: {wl['cfg']} -- {wl['w']}x{wl['h']} yuv420p {wl['bpc']}-bit, model {wl['model']}"
+                        + (" + psnr" if wl["psnr"] else "") + (" + float_ssim" if wl["ssim"] else "")
+                        + (" + float_ms_ssim" if wl["ms_ssim"] else ""),
+            "frames_per_step_per_gpu": fps, "pool_frames_per_gpu": wl["pool"],
+            "l2_policy": "inputs larger than L2: each step streams the whole resident pool "
+                         f"({wl['pool']} frame pairs, {wl['pool'] * 2 * wl['w'] * wl['h'] * (1 if wl['bpc'] == 8 else 2) / 1e6:.0f} MB of luma) "
+                         "through the kernels",
+            "parallelism": f"frame-sharded x{n_gpus}, no collective"}
+
+
+# --------------------------------------------------------------------------------------------
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--frames-per-step", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from pqa2_b200 import _lib as L
+    from pqa2_b200 import engine, model as M, synth
+    from pqa2_b200.extractor import DeviceBuffer, FeatureExtractor, pinned_empty
+
+    wname = args.workload
+    if wname == "auto":
+        wname = "1080p-float"
+    wl = WORKLOADS[wname]
+
+    if args.impl == "reference":
+        return reference_arm(args, wl, wname)
+
+    lib = L.load()
+    if lib.bv_device_count() <= local:
+        raise SystemExit("bench.py: no CUDA device for this rank (the engine has no CPU fallback)")
+    if wname == "1080p-float" and args.workload == "auto":
+        # the float extractors must exist; otherwise say so loudly instead of measuring something else
+        try:
+            FeatureExtractor(64, 64, 8, 0, L.FEAT_VMAF_FLOAT, local).close()
+        except Exception as e:
+            raise SystemExit(f"bench.py: float extractors unavailable: {e}")
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w, h, bpc = wl["w"], wl["h"], wl["bpc"]
+    bps = 1 if bpc == 8 else 2
+    fps_step = args.frames_per_step or wl["frames_per_step"]
+    P = wl["pool"]
+    model = M.resolve_model(wl["model"])
+    opt = engine.EngineOptions(psnr=wl["psnr"], ssim=wl["ssim"], ms_ssim=wl["ms_ssim"], devices=(local,))
+    mask = engine.feature_mask(model, opt)
+
+    # ---- synthetic clip: P frame pairs (luma only: every enabled feature reads luma), pinned on the
+    #      host (e2e) and resident in HBM (value)
+    t0 = time.perf_counter()
+    plane = w * h * bps
+    dtype = np.uint8 if bpc == 8 else np.uint16
+    host_ref = [pinned_empty((h, w), dtype) for _ in range(P)]
+    host_dis = [pinned_empty((h, w), dtype) for _ in range(P)]
+    dev = DeviceBuffer(2 * P * plane, local)
+    for i in range(P):
+        rp, dp = synth.frame_pair(100 + rank, i, w, h, bpc, chroma=False)
+        host_ref[i][...] = rp[0]
+        host_dis[i][...] = dp[0]
+        dev.upload((2 * i) * plane, host_ref[i])
+        dev.upload((2 * i + 1) * plane, host_dis[i])
+    if rank == 0:
+        log(f"[bench] synthesised {P} frame pairs {w}x{h} {bpc}-bit in {time.perf_counter() - t0:.1f}s")
+
+    fx = FeatureExtractor(w, h, bpc, 0, mask, local, vif_enhn_gain_limit=model.vif_enhn_gain_limit,
+                          adm_enhn_gain_limit=model.adm_enhn_gain_limit)
+    pitch = w * bps
+    counter = [0]
+
+    def run_step():
+        for _ in range(fps_step):
+            i = counter[0]
+            k = i % P
+            fx.submit_device(i, [(dev.ptr + (2 * k) * plane, pitch)], [(dev.ptr + (2 * k + 1) * plane, pitch)],
+                             L.FRAME_FIRST if i == 0 else 0)
+            counter[0] += 1
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident run: W warm-up steps, then exactly K timed steps
+    for _ in range(max(args.warmup, 3)):
+        run_step()
+    fx.flush()
+    sampler = ClockSampler(local)
+    barrier()
+    fx.flush()
+    launches0 = fx.kernel_launches
+    sampler.start()
+    fx.timer_mark(0)
+    for _ in range(args.steps):
+        run_step()
+    fx.timer_mark(1)
+    fx.flush()
+    ms = fx.timer_elapsed_ms()
+    barrier()
+    clocks = sampler.stop()
+    launches = fx.kernel_launches - launches0
+    ms = max_over_ranks(ms)
+    total_frames = fps_step * args.steps * world
+    value = total_frames / (ms / 1000.0)
+
+    # ---- per-kernel profile over the same region (events around every launch; a separate pass so the
+    #      event overhead stays out of `value`)
+    fx.set_profiling(True)
+    fx.kernel_profile(reset=True)
+    for _ in range(min(args.steps, 10)):
+        run_step()
+    fx.flush()
+    prof = fx.kernel_profile(reset=True)
+    fx.set_profiling(False)
+    results_sample = fx.fetch(0, 1)
+    peak, peak_src = measured_peaks()
+    B = L.BV_MAX_BATCH
+    kernels = {}
+    for nm, (kms, cnt) in prof.items():
+        per_launch_ms = kms / cnt
+        by = kernel_bytes(nm, w, h, bps)
+        kernels[nm] = {"ms_per_launch": per_launch_ms, "launches": cnt,
+                       "gbps": (by * B / (per_launch_ms * 1e-3) / 1e9) if by else None}
+    tot_ms = sum(k["ms_per_launch"] for k in kernels.values()) or 1.0
+    top = max(kernels, key=lambda n: kernels[n]["ms_per_launch"]) if kernels else None
+    roofline = None
+    if top:
+        by = kernel_bytes(top, w, h, bps)
+        ach = kernels[top]["gbps"]
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": by * B if by else None,
+                    "ms_per_launch": kernels[top]["ms_per_launch"], "frames_per_launch": B,
+                    "share_of_step": kernels[top]["ms_per_launch"] / tot_ms,
+                    "pipeline_floor_gbps": 2 * plane * value / world / 1e9,
+                    "pipeline_floor_frac": 2 * plane * value / world / 1e9 / peak}
+    fx.close()
+
+    # ---- end to end through the public engine call: pinned host frames in, scores out
+    e2e = None
+    if not args.no_e2e:
+        class PinnedClip(engine.FrameSource):
+            zero_copy = True
+
+            def __init__(self, n):
+                self.width, self.height, self.bpc, self.chroma, self.nb_frames, self.fps = w, h, bpc, 0, n, 30.0
+
+            def get(self, i, luma_only):
+                return [host_ref[i % P]], [host_dis[i % P]]
+
+        n_e2e = fps_step * max(1, min(args.steps, 8))
+        engine.analyze(PinnedClip(min(n_e2e, 2 * B)), model, opt)            # warm-up (allocations, first launches)
+        barrier()
+        t0 = time.perf_counter()
+        res = engine.analyze(PinnedClip(n_e2e), model, opt)
+        dt = time.perf_counter() - t0
+        dt = max_over_ranks(dt)
+        steps_e2e = n_e2e / fps_step
+        e2e = {"value": n_e2e * world / dt, "unit": "frames/s",
+               "h2d_bytes_per_step": int(2 * plane * fps_step + 6 * 8 * fps_step),
+               "d2h_bytes_per_step": int((L.BV_RAW_WORDS * 8 + 64 * 8 + 8) * fps_step),
+               "frames": n_e2e, "steps": steps_e2e,
+               "timer": "host wall clock around engine.analyze (H2D, kernels, feature D2H, SVR, pooling), max over ranks",
+               "pooled_vmaf_mean": res["pooled_metrics"]["vmaf"]["mean"]}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    base = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            base = cpu_baseline(wl)
+        except Exception as e:          # the baseline is a report, never a reason to lose the GPU numbers
+            base = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+    out = {"metric": "vmaf_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": wl_dtype(wl), "data": "synthetic",
+           "config": bench_config(wl, wname, fps_step, world), "clocks": clocks, "e2e": e2e,
+           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": base,
+           "kernels": {k: {"ms_per_launch": round(v["ms_per_launch"], 5), "gbps": v["gbps"] and round(v["gbps"], 1),
+                           "frac_of_hbm_peak": v["gbps"] and round(v["gbps"] / peak, 4)} for k, v in kernels.items()},
+           "published_reference_fps": "23-26 fps (1080p, libvmaf n_threads=4, decode included; BASELINE.md §1)"}
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -125,12 +125,18 @@ int64_t bv_frames_done(bv_ctx *);        /* frames whose features are ready (non
 int  bv_fetch(bv_ctx *, int64_t first, int64_t count, bv_frame_features *out);
 int  bv_cancel(bv_ctx *);                /* thread-safe; subsequent calls fail with BV_ERR_CANCELLED */
 int64_t bv_kernel_launches(bv_ctx *);    /* kernels launched by this ctx so far (bench `gpu_launches`) */
-/* CUDA-event time (ms) spent in the named kernel family since the last call with reset != 0.
- * families: 0 motion, 1 vif, 2 adm, 3 psnr, 4 float vif, 5 float adm, 6 float motion,
- * 7 float_ssim / float_ms_ssim; requires bv_set_profiling(ctx, 1). */
+/* Per-kernel CUDA-event profiling (events on the compute stream around every launch).  Enable with
+ * bv_set_profiling(ctx, 1); ids run 0 .. bv_kernel_slots()-1, bv_kernel_name(id) is NULL for unused
+ * ids.  bv_kernel_ms = accumulated device time, bv_kernel_count = launches timed. */
 int  bv_set_profiling(bv_ctx *, int enable);
-double bv_family_ms(bv_ctx *, int family, int reset);
-double bv_family_launches(bv_ctx *, int family);
+int  bv_kernel_slots(void);
+const char *bv_kernel_name(int id);
+double bv_kernel_ms(bv_ctx *, int id, int reset);
+double bv_kernel_count(bv_ctx *, int id, int reset);
+/* Device stopwatch on the compute stream: mark(0) before the first submit of a timed region, mark(1)
+ * after the last (launches any partial group first); elapsed blocks until mark(1) has happened. */
+int  bv_timer_mark(bv_ctx *, int which);
+double bv_timer_elapsed_ms(bv_ctx *);
 
 #define BV_ERR_ARG        -1
 #define BV_ERR_CUDA       -2

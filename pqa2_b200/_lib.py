@@ -67,7 +67,8 @@ EXPORTS = (
     "bv_abi_version", "bv_device_count", "bv_create", "bv_destroy", "bv_last_error", "bv_pinned_alloc",
     "bv_pinned_free", "bv_device_alloc", "bv_device_free", "bv_device_upload", "bv_sizeof_frame_features",
     "bv_submit", "bv_submit_device", "bv_wait_uploads", "bv_flush", "bv_frames_done", "bv_fetch", "bv_cancel",
-    "bv_kernel_launches", "bv_set_profiling", "bv_family_ms", "bv_family_launches",
+    "bv_kernel_launches", "bv_set_profiling", "bv_kernel_slots", "bv_kernel_name", "bv_kernel_ms", "bv_kernel_count",
+    "bv_timer_mark", "bv_timer_elapsed_ms",
     "bv_model_create", "bv_model_free", "bv_predict", "bv_predict_device",
 )
 
@@ -118,10 +119,16 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.bv_kernel_launches.argtypes = [vp]
     L.bv_kernel_launches.restype = i64
     L.bv_set_profiling.argtypes = [vp, i]
-    L.bv_family_ms.argtypes = [vp, i, i]
-    L.bv_family_ms.restype = d
-    L.bv_family_launches.argtypes = [vp, i]
-    L.bv_family_launches.restype = d
+    L.bv_kernel_slots.restype = i
+    L.bv_kernel_name.argtypes = [i]
+    L.bv_kernel_name.restype = C.c_char_p
+    L.bv_kernel_ms.argtypes = [vp, i, i]
+    L.bv_kernel_ms.restype = d
+    L.bv_kernel_count.argtypes = [vp, i, i]
+    L.bv_kernel_count.restype = d
+    L.bv_timer_mark.argtypes = [vp, i]
+    L.bv_timer_elapsed_ms.argtypes = [vp]
+    L.bv_timer_elapsed_ms.restype = d
     L.bv_model_create.argtypes = [i, i, pd, pd, d, d, pd, pd, pd, i, pd, u]
     L.bv_model_create.restype = vp
     L.bv_model_free.argtypes = [vp]

@@ -505,11 +505,11 @@ void bv_adm_finish_scale(const BvAdmScaleParams &p, int scale, double view_dist,
 }
 
 void bv_launch_adm(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, const BvAdmBuffers &ab,
-                   const BvAdmScaleParams sp[4], double egl, unsigned long long *raw, cudaStream_t st,
-                   long long *nlaunch)
+                   const BvAdmScaleParams sp[4], double egl, unsigned long long *raw, const BvLaunch &L)
 {
     const float cos_1deg_sq = (float)(cos(1.0 * M_PI / 180.0) * cos(1.0 * M_PI / 180.0));
     BvPlane cr = ref_y, cd = dis_y;
+    cudaStream_t st = L.st;
     for (int s = 0; s < 4; ++s) {
         AdmArgs a;
         a.ref = cr; a.dis = cd;
@@ -519,6 +519,7 @@ void bv_launch_adm(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, cons
         a.a_dis = s < 3 ? static_cast<uint8_t *>(ab.bands[s]) + (size_t)BV_MAX_BATCH * ab.band_plane_elems[s] * esz : nullptr;
         a.sp = sp[s]; a.bpc = bpc; a.div_lookup = ab.div_lookup; a.egl = egl; a.cos_1deg_sq = cos_1deg_sq;
         a.rows = ab.rows; a.rows_frame_stride = ab.rows_frame_stride; a.rows_offset = ab.rows_scale_offset[s];
+        bv_prof_begin(L, BVK_ADM_S0 + s);
         switch (s) {
         case 0:
             if (bpc == 8) launch_scale<0, uint8_t>(b, a, st); else launch_scale<0, uint16_t>(b, a, st);
@@ -527,7 +528,7 @@ void bv_launch_adm(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, cons
         case 2: launch_scale<2, int32_t>(b, a, st); break;
         default: launch_scale<3, int32_t>(b, a, st); break;
         }
-        ++*nlaunch;
+        bv_prof_end(L, BVK_ADM_S0 + s);
         if (s < 3) {
             cr = bv_plane_contig(a.a_ref, (size_t)sp[s].w * esz, ab.band_plane_elems[s] * esz, b.n);
             cd = bv_plane_contig(a.a_dis, (size_t)sp[s].w * esz, ab.band_plane_elems[s] * esz, b.n);
@@ -536,6 +537,7 @@ void bv_launch_adm(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, cons
     AdmFinishArgs fa;
     for (int s = 0; s < 4; ++s) { fa.sp[s] = sp[s]; fa.rows_offset[s] = ab.rows_scale_offset[s]; }
     fa.rows = ab.rows; fa.rows_frame_stride = ab.rows_frame_stride; fa.raw = raw;
+    bv_prof_begin(L, BVK_ADM_FINISH);
     adm_rows_finish_kernel<<<dim3(4, b.n), 128, 0, st>>>(b, fa);
-    ++*nlaunch;
+    bv_prof_end(L, BVK_ADM_FINISH);
 }

@@ -28,7 +28,14 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr int N_SLOTS = 3;          // frame groups in flight (upload / compute / readback)
-constexpr int N_FAMILIES = 8;
+
+const char *const k_kernel_names[BV_MAX_KERNELS] = {
+    "motion_blur", "motion_sad",
+    "vif_stat_s0", "vif_subsample_s1", "vif_stat_s1", "vif_subsample_s2", "vif_stat_s2", "vif_subsample_s3", "vif_stat_s3",
+    "adm_scale0", "adm_scale1", "adm_scale2", "adm_scale3", "adm_rows_finish",
+    "psnr_sse_y", "psnr_sse_u", "psnr_sse_v",
+    "ffssim_y", "ffssim_u", "ffssim_v",
+};
 
 struct Group {
     int n = 0;
@@ -45,9 +52,8 @@ struct Group {
     unsigned long long *d_raw = nullptr, *h_raw = nullptr;     // [B][BV_RAW_WORDS]
     double *d_fraw = nullptr, *h_fraw = nullptr;               // [B][BV_FRAW_WORDS]
     cudaEvent_t uploaded = nullptr, done = nullptr;
-    cudaEvent_t fam_ev[N_FAMILIES + 1] = {};
+    BvProf prof;
     bool in_flight = false;
-    bool profiled = false;
 };
 
 }  // namespace
@@ -68,8 +74,10 @@ struct bv_ctx {
     std::string err;
     long long nlaunch = 0;
     bool profiling = false;
-    double fam_ms[N_FAMILIES] = {};
-    double fam_launch[N_FAMILIES] = {};
+    double k_ms[BV_MAX_KERNELS] = {};
+    double k_count[BV_MAX_KERNELS] = {};
+    cudaEvent_t t_ev[2] = { nullptr, nullptr };      // bv_timer_mark
+    bool t_set[2] = { false, false };
     size_t staging_pitch[3] = { 0, 0, 0 };
     size_t staging_frame_bytes[3] = { 0, 0, 0 };
 
@@ -129,8 +137,9 @@ int alloc_ctx(bv_ctx *c)
         CK(cudaHostAlloc(&g.h_fraw, sizeof(double) * B * BV_FRAW_WORDS, cudaHostAllocDefault));
         CK(cudaEventCreateWithFlags(&g.uploaded, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
-        for (int k = 0; k <= N_FAMILIES; ++k) CK(cudaEventCreate(&g.fam_ev[k]));
+        memset(&g.prof, 0, sizeof g.prof);
     }
+    for (int k = 0; k < 2; ++k) CK(cudaEventCreate(&c->t_ev[k]));
     const size_t npx = (size_t)c->w * c->h;
     if (c->feat & BV_FEAT_MOTION) {
         c->blur_elems = (npx + 7) & ~(size_t)7;      // frames stay 16-byte aligned for the uint4 SAD loads
@@ -268,11 +277,17 @@ int harvest(bv_ctx *c, Group &g)
 {
     if (!g.in_flight) return 0;
     CK(cudaEventSynchronize(g.done));
-    if (g.profiled) {
-        for (int k = 0; k < N_FAMILIES; ++k) {
+    if (g.prof.on) {
+        for (int k = 0; k < BV_MAX_KERNELS; ++k) {
+            if (!g.prof.used[k]) continue;
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, g.fam_ev[k], g.fam_ev[k + 1]) == cudaSuccess) c->fam_ms[k] += ms;
+            if (cudaEventElapsedTime(&ms, g.prof.ev[k][0], g.prof.ev[k][1]) == cudaSuccess) {
+                c->k_ms[k] += ms;
+                c->k_count[k] += 1.0;
+            }
+            g.prof.used[k] = false;
         }
+        g.prof.on = false;
     }
     if ((int64_t)c->results.size() < g.first_ordinal + g.n) c->results.resize(g.first_ordinal + g.n);
     for (int f = 0; f < g.n; ++f) finish_frame(c, g, f, c->results[g.first_ordinal + f]);
@@ -307,52 +322,34 @@ int launch_group(bv_ctx *c, Group &g)
     CK(cudaMemsetAsync(g.d_raw, 0, sizeof(unsigned long long) * g.n * BV_RAW_WORDS, st));
     CK(cudaMemsetAsync(g.d_fraw, 0, sizeof(double) * g.n * BV_FRAW_WORDS, st));
     const BvPlane ry = group_plane(g, 0, 0), dy = group_plane(g, 1, 0);
-    const bool prof = c->profiling;
-    g.profiled = prof;
-    int fam = 0;
-    auto mark = [&](int k) { if (prof) cudaEventRecord(g.fam_ev[k], st); };
-    long long before;
+    if (c->profiling && !g.prof.have_events) {
+        for (int k = 0; k < BV_MAX_KERNELS; ++k) { CK(cudaEventCreate(&g.prof.ev[k][0])); CK(cudaEventCreate(&g.prof.ev[k][1])); }
+        g.prof.have_events = true;
+    }
+    g.prof.on = c->profiling;
+    const BvLaunch L = { st, &g.prof, &c->nlaunch };
 
-    mark(fam++);                                                 // 0: motion
-    before = c->nlaunch;
     if (c->feat & BV_FEAT_MOTION) {
         uint16_t *cur = c->blur[c->blur_cur];
         const uint16_t *prev_last = c->blur_prev_n > 0
             ? c->blur[c->blur_cur ^ 1] + (size_t)(c->blur_prev_n - 1) * c->blur_elems : cur;
-        bv_launch_motion_blur(b, ry, c->bpc, c->w, c->h, cur, c->blur_elems, st, &c->nlaunch);
-        bv_launch_motion_sad(b, cur, prev_last, c->blur_elems, c->w, c->h, g.d_raw, st, &c->nlaunch);
+        bv_launch_motion_blur(b, ry, c->bpc, c->w, c->h, cur, c->blur_elems, L);
+        bv_launch_motion_sad(b, cur, prev_last, c->blur_elems, c->w, c->h, g.d_raw, L);
         c->blur_prev_n = g.n;
         c->blur_cur ^= 1;
     }
-    c->fam_launch[0] += (double)(c->nlaunch - before);
-    mark(fam++);                                                 // 1: vif
-    before = c->nlaunch;
     if (c->feat & BV_FEAT_VIF)
-        bv_launch_vif(b, ry, dy, c->bpc, c->vif_lv, c->d_log2, c->opts.vif_enhn_gain_limit, g.d_raw, st, &c->nlaunch);
-    c->fam_launch[1] += (double)(c->nlaunch - before);
-    mark(fam++);                                                 // 2: adm
-    before = c->nlaunch;
+        bv_launch_vif(b, ry, dy, c->bpc, c->vif_lv, c->d_log2, c->opts.vif_enhn_gain_limit, g.d_raw, L);
     if (c->feat & BV_FEAT_ADM) {
         CK(cudaMemsetAsync(c->adm.rows, 0, sizeof(unsigned long long) * c->adm.rows_frame_stride * g.n, st));
-        bv_launch_adm(b, ry, dy, c->bpc, c->adm, c->adm_sp, c->opts.adm_enhn_gain_limit, g.d_raw, st, &c->nlaunch);
+        bv_launch_adm(b, ry, dy, c->bpc, c->adm, c->adm_sp, c->opts.adm_enhn_gain_limit, g.d_raw, L);
     }
-    c->fam_launch[2] += (double)(c->nlaunch - before);
-    mark(fam++);                                                 // 3: psnr
-    before = c->nlaunch;
     if (c->feat & BV_FEAT_PSNR_Y)
-        bv_launch_sse(b, ry, dy, c->bpc, c->w, c->h, 0, g.d_raw, st, &c->nlaunch);
+        bv_launch_sse(b, ry, dy, c->bpc, c->w, c->h, 0, g.d_raw, L);
     if ((c->feat & BV_FEAT_PSNR_UV) && needs_chroma(c))
         for (int p = 1; p < 3; ++p)
-            bv_launch_sse(b, group_plane(g, 0, p), group_plane(g, 1, p), c->bpc, c->cw, c->ch, p, g.d_raw, st,
-                          &c->nlaunch);
-    c->fam_launch[3] += (double)(c->nlaunch - before);
-    mark(fam++);                                                 // 4..7: float families
-    if (c->fl) {
-        cudaEvent_t *evs = prof ? g.fam_ev + 4 : nullptr;
-        bv_float_launch(c->fl, b, ry, dy, g.d_fraw, st, &c->nlaunch, evs, c->fam_launch + 4);
-    } else if (prof) {
-        for (int k = 5; k <= N_FAMILIES; ++k) cudaEventRecord(g.fam_ev[k], st);
-    }
+            bv_launch_sse(b, group_plane(g, 0, p), group_plane(g, 1, p), c->bpc, c->cw, c->ch, p, g.d_raw, L);
+    if (c->fl) bv_float_launch(c->fl, b, ry, dy, g.d_fraw, L);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(g.h_raw, g.d_raw, sizeof(unsigned long long) * g.n * BV_RAW_WORDS, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(g.h_fraw, g.d_fraw, sizeof(double) * g.n * BV_FRAW_WORDS, cudaMemcpyDeviceToHost, st));
@@ -484,7 +481,8 @@ void bv_destroy(bv_ctx *c)
         if (g.h_fraw) cudaFreeHost(g.h_fraw);
         if (g.uploaded) cudaEventDestroy(g.uploaded);
         if (g.done) cudaEventDestroy(g.done);
-        for (int k = 0; k <= N_FAMILIES; ++k) if (g.fam_ev[k]) cudaEventDestroy(g.fam_ev[k]);
+        if (g.prof.have_events)
+            for (int k = 0; k < BV_MAX_KERNELS; ++k) { cudaEventDestroy(g.prof.ev[k][0]); cudaEventDestroy(g.prof.ev[k][1]); }
     }
     for (int k = 0; k < 2; ++k) if (c->blur[k]) cudaFree(c->blur[k]);
     if (c->d_log2) cudaFree(c->d_log2);
@@ -492,6 +490,7 @@ void bv_destroy(bv_ctx *c)
     if (c->feat & BV_FEAT_ADM) { for (int s = 0; s < 3; ++s) if (c->adm.bands[s]) cudaFree(c->adm.bands[s]); if (c->adm.rows) cudaFree(c->adm.rows); }
     if (c->d_div) cudaFree(c->d_div);
     if (c->fl) bv_float_destroy(c->fl);
+    for (int k = 0; k < 2; ++k) if (c->t_ev[k]) cudaEventDestroy(c->t_ev[k]);
     if (c->up) cudaStreamDestroy(c->up);
     if (c->comp) cudaStreamDestroy(c->comp);
     delete c;
@@ -596,18 +595,55 @@ int bv_set_profiling(bv_ctx *c, int enable)
     return 0;
 }
 
-double bv_family_ms(bv_ctx *c, int family, int reset)
+int bv_kernel_slots(void) { return BV_MAX_KERNELS; }
+
+const char *bv_kernel_name(int id)
 {
-    if (!c || family < 0 || family >= N_FAMILIES) return -1.0;
-    const double v = c->fam_ms[family];
-    if (reset) c->fam_ms[family] = 0.0;
+    if (id < 0 || id >= BV_MAX_KERNELS) return nullptr;
+    if (id >= BVK_F_FIRST) return bv_float_kernel_name(id);
+    return k_kernel_names[id];
+}
+
+double bv_kernel_ms(bv_ctx *c, int id, int reset)
+{
+    if (!c || id < 0 || id >= BV_MAX_KERNELS) return -1.0;
+    const double v = c->k_ms[id];
+    if (reset) c->k_ms[id] = 0.0;
     return v;
 }
 
-double bv_family_launches(bv_ctx *c, int family)
+double bv_kernel_count(bv_ctx *c, int id, int reset)
 {
-    if (!c || family < 0 || family >= N_FAMILIES) return -1.0;
-    return c->fam_launch[family];
+    if (!c || id < 0 || id >= BV_MAX_KERNELS) return -1.0;
+    const double v = c->k_count[id];
+    if (reset) c->k_count[id] = 0.0;
+    return v;
+}
+
+// Device-side stopwatch on the compute stream: mark(0) before the first submit of a timed region,
+// mark(1) after the last; elapsed = time between the two marks as the GPU saw them.
+int bv_timer_mark(bv_ctx *c, int which)
+{
+    if (!c || which < 0 || which > 1) return BV_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    if (which == 1) {
+        // everything submitted so far must be in the stream before the end mark
+        Group &g = c->groups[c->cur];
+        if (!g.in_flight && g.n > 0) { int rc = launch_group(c, g); if (rc) return rc; }
+    }
+    CK(cudaEventRecord(c->t_ev[which], c->comp));
+    c->t_set[which] = true;
+    return 0;
+}
+
+double bv_timer_elapsed_ms(bv_ctx *c)
+{
+    if (!c || !c->t_set[0] || !c->t_set[1]) return -1.0;
+    cudaSetDevice(c->device);
+    if (cudaEventSynchronize(c->t_ev[1]) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->t_ev[0], c->t_ev[1]) != cudaSuccess) return -1.0;
+    return (double)ms;
 }
 
 size_t bv_sizeof_frame_features(void) { return sizeof(bv_frame_features); }

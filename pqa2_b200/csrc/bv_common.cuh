@@ -107,15 +107,44 @@ struct BvAdmScaleParams {
     int den_sh_row; unsigned long long den_add_row;
 };
 
+// ---- per-kernel profiling (CUDA events on the launching stream) ----------------------------
+enum BvKernelId {
+    BVK_MOTION_BLUR = 0, BVK_MOTION_SAD,
+    BVK_VIF_STAT0, BVK_VIF_SUB1, BVK_VIF_STAT1, BVK_VIF_SUB2, BVK_VIF_STAT2, BVK_VIF_SUB3, BVK_VIF_STAT3,
+    BVK_ADM_S0, BVK_ADM_S1, BVK_ADM_S2, BVK_ADM_S3, BVK_ADM_FINISH,
+    BVK_SSE_Y, BVK_SSE_U, BVK_SSE_V,
+    BVK_FFSSIM_Y, BVK_FFSSIM_U, BVK_FFSSIM_V,
+    BVK_F_FIRST,                       // float kernels: ids BVK_F_FIRST .. BV_MAX_KERNELS-1 (bv_float.cuh)
+    BV_MAX_KERNELS = 64
+};
+struct BvProf {
+    bool on = false;
+    bool have_events = false;
+    cudaEvent_t ev[BV_MAX_KERNELS][2];
+    bool used[BV_MAX_KERNELS];
+};
+struct BvLaunch {
+    cudaStream_t st;
+    BvProf *prof;
+    long long *nlaunch;
+};
+static inline void bv_prof_begin(const BvLaunch &l, int id)
+{
+    if (l.prof && l.prof->on) { cudaEventRecord(l.prof->ev[id][0], l.st); l.prof->used[id] = true; }
+}
+static inline void bv_prof_end(const BvLaunch &l, int id)
+{
+    if (l.prof && l.prof->on) cudaEventRecord(l.prof->ev[id][1], l.st);
+    ++*l.nlaunch;
+}
+
 // ---- kernel launchers (one per .cu file) ---------------------------------------------------
-struct BvLaunchStats { long long launches; };
 
 // motion
 void bv_launch_motion_blur(const BvBatch &b, BvPlane ref_y, int bpc, int w, int h, uint16_t *blur_cur,
-                           size_t blur_frame_elems, cudaStream_t st, long long *nlaunch);
+                           size_t blur_frame_elems, const BvLaunch &L);
 void bv_launch_motion_sad(const BvBatch &b, const uint16_t *blur_cur, const uint16_t *blur_prev_group_last,
-                          size_t blur_frame_elems, int w, int h, unsigned long long *raw, cudaStream_t st,
-                          long long *nlaunch);
+                          size_t blur_frame_elems, int w, int h, unsigned long long *raw, const BvLaunch &L);
 // vif
 struct BvVifLevels {                        // u16 pyramid levels 1..3 (tight pitch), ref and dis
     uint16_t *ref[4], *dis[4];              // [0] unused
@@ -123,8 +152,7 @@ struct BvVifLevels {                        // u16 pyramid levels 1..3 (tight pi
     int w[4], h[4];
 };
 void bv_launch_vif(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, const BvVifLevels &lv,
-                   const uint16_t *log2_table, double egl, unsigned long long *raw, cudaStream_t st,
-                   long long *nlaunch);
+                   const uint16_t *log2_table, double egl, unsigned long long *raw, const BvLaunch &L);
 // adm
 struct BvAdmBuffers {
     void *bands[4];                         // scale s: [frame][ref/dis][a,v,h,d][h][w], i16 (s=0) / i32
@@ -135,11 +163,10 @@ struct BvAdmBuffers {
     const int *div_lookup;                  // 65537 entries
 };
 void bv_launch_adm(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, const BvAdmBuffers &ab,
-                   const BvAdmScaleParams sp[4], double egl, unsigned long long *raw, cudaStream_t st,
-                   long long *nlaunch);
+                   const BvAdmScaleParams sp[4], double egl, unsigned long long *raw, const BvLaunch &L);
 // psnr
 void bv_launch_sse(const BvBatch &b, BvPlane ref, BvPlane dis, int bpc, int w, int h, int plane_idx,
-                   unsigned long long *raw, cudaStream_t st, long long *nlaunch);
+                   unsigned long long *raw, const BvLaunch &L);
 // adm host-side helpers (bv_adm.cu)
 void bv_adm_rfactor(int scale, double view_dist, int display_h, float rf[3]);
 void bv_adm_make_params(int w, int h, double view_dist, int display_h, BvAdmScaleParams sp[4]);

@@ -16,8 +16,8 @@
 struct BvFloatState;
 BvFloatState *bv_float_create(int w, int h, int bpc, unsigned feat, int batch, const bv_opts *opts);
 void bv_float_destroy(BvFloatState *);
-// evs: 5 events bounding families 4..7 (float vif, float adm, float motion, ssim/ms-ssim) or nullptr.
 void bv_float_launch(BvFloatState *, const BvBatch &b, BvPlane ref_y, BvPlane dis_y, double *d_fraw,
-                     cudaStream_t st, long long *nlaunch, cudaEvent_t *evs, double *fam_launch);
+                     const BvLaunch &L);
+const char *bv_float_kernel_name(int id);     // ids >= BVK_F_FIRST
 // Host finalisation of one frame; returns the BV_FEAT_* bits it filled.
 unsigned bv_float_finish(BvFloatState *, const double *fraw, unsigned frame_flags, bv_frame_features *o);

@@ -91,14 +91,15 @@ svr_predict_kernel(const double *__restrict__ feat, int n_feat, const double *__
 }  // namespace
 
 void bv_launch_sse(const BvBatch &b, BvPlane ref, BvPlane dis, int bpc, int w, int h, int plane_idx,
-                   unsigned long long *raw, cudaStream_t st, long long *nlaunch)
+                   unsigned long long *raw, const BvLaunch &L)
 {
     int gx = (h + 7) / 8;
     if (gx > 148) gx = 148;
     dim3 grid(gx, b.n);
-    if (bpc == 8) sse_kernel<uint8_t><<<grid, 256, 0, st>>>(b, ref, dis, w, h, raw, BV_RAW_SSE + plane_idx);
-    else sse_kernel<uint16_t><<<grid, 256, 0, st>>>(b, ref, dis, w, h, raw, BV_RAW_SSE + plane_idx);
-    ++*nlaunch;
+    bv_prof_begin(L, BVK_SSE_Y + plane_idx);
+    if (bpc == 8) sse_kernel<uint8_t><<<grid, 256, 0, L.st>>>(b, ref, dis, w, h, raw, BV_RAW_SSE + plane_idx);
+    else sse_kernel<uint16_t><<<grid, 256, 0, L.st>>>(b, ref, dis, w, h, raw, BV_RAW_SSE + plane_idx);
+    bv_prof_end(L, BVK_SSE_Y + plane_idx);
 }
 
 void bv_launch_svr(const double *d_feat, int n_feat, const double *d_slopes, const double *d_intercepts,

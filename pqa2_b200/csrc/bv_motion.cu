@@ -95,25 +95,26 @@ motion_sad_kernel(BvBatch batch, const uint16_t *__restrict__ blur, const uint16
 }  // namespace
 
 void bv_launch_motion_blur(const BvBatch &b, BvPlane ref_y, int bpc, int w, int h, uint16_t *blur_cur,
-                           size_t blur_frame_elems, cudaStream_t st, long long *nlaunch)
+                           size_t blur_frame_elems, const BvLaunch &L)
 {
     dim3 grid((w + MB_TW - 1) / MB_TW, (h + MB_TH - 1) / MB_TH, b.n);
+    bv_prof_begin(L, BVK_MOTION_BLUR);
     if (bpc == 8)
-        motion_blur_kernel<uint8_t><<<grid, 256, 0, st>>>(b, ref_y, bpc, w, h, blur_cur, blur_frame_elems);
+        motion_blur_kernel<uint8_t><<<grid, 256, 0, L.st>>>(b, ref_y, bpc, w, h, blur_cur, blur_frame_elems);
     else
-        motion_blur_kernel<uint16_t><<<grid, 256, 0, st>>>(b, ref_y, bpc, w, h, blur_cur, blur_frame_elems);
-    ++*nlaunch;
+        motion_blur_kernel<uint16_t><<<grid, 256, 0, L.st>>>(b, ref_y, bpc, w, h, blur_cur, blur_frame_elems);
+    bv_prof_end(L, BVK_MOTION_BLUR);
 }
 
 void bv_launch_motion_sad(const BvBatch &b, const uint16_t *blur_cur, const uint16_t *blur_prev_group_last,
-                          size_t blur_frame_elems, int w, int h, unsigned long long *raw, cudaStream_t st,
-                          long long *nlaunch)
+                          size_t blur_frame_elems, int w, int h, unsigned long long *raw, const BvLaunch &L)
 {
     const size_t n = (size_t)w * h;
     int gx = (int)((n / 8 + 255) / 256);
     if (gx > 148 * 2) gx = 148 * 2;
     if (gx < 1) gx = 1;
     dim3 grid(gx, b.n);
-    motion_sad_kernel<<<grid, 256, 0, st>>>(b, blur_cur, blur_prev_group_last, blur_frame_elems, n, raw);
-    ++*nlaunch;
+    bv_prof_begin(L, BVK_MOTION_SAD);
+    motion_sad_kernel<<<grid, 256, 0, L.st>>>(b, blur_cur, blur_prev_group_last, blur_frame_elems, n, raw);
+    bv_prof_end(L, BVK_MOTION_SAD);
 }

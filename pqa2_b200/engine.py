@@ -148,19 +148,22 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
         ctx_holder.append(fx)
         with fx:
             B = opt.batch_frames or L.BV_MAX_BATCH
-            ring = [([pinned_empty(s, dtype) for s in shapes], [pinned_empty(s, dtype) for s in shapes])
-                    for _ in range(2 * B)]
+            zero_copy = bool(getattr(handle, "zero_copy", False))
+            ring = [] if zero_copy else [([pinned_empty(s, dtype) for s in shapes],
+                                          [pinned_empty(s, dtype) for s in shapes]) for _ in range(2 * B)]
             lead = 1 if start > 0 else 0
             ordinal = 0
             for i in range(start - lead, end):
                 if cancel.is_set():
                     fx.cancel()
                     raise _Cancelled()
-                slot = ordinal % len(ring)
-                if ordinal and ordinal % B == 0:
-                    fx.wait_uploads()           # the half of the ring we are about to overwrite is free again
-                rp, dp = ring[slot]
-                handle.read_into(i, rp, dp, luma_only)
+                if zero_copy:
+                    rp, dp = handle.get(i, luma_only)     # caller-owned (pinned) planes, valid until we return
+                else:
+                    if ordinal and ordinal % B == 0:
+                        fx.wait_uploads()       # the half of the ring we are about to overwrite is free again
+                    rp, dp = ring[ordinal % len(ring)]
+                    handle.read_into(i, rp, dp, luma_only)
                 flags = 0
                 if i < start:
                     flags |= L.FRAME_LEAD_IN

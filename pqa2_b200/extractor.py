@@ -134,11 +134,24 @@ class FeatureExtractor:
     def set_profiling(self, on: bool):
         self.lib.bv_set_profiling(self._ctx, 1 if on else 0)
 
-    def family_ms(self, family: int, reset: bool = False) -> float:
-        return float(self.lib.bv_family_ms(self._ctx, family, 1 if reset else 0))
+    def kernel_profile(self, reset: bool = True) -> dict:
+        """{kernel name: (total ms, launches timed)} since the last reset (needs set_profiling(True))."""
+        out = {}
+        for k in range(self.lib.bv_kernel_slots()):
+            nm = self.lib.bv_kernel_name(k)
+            if not nm:
+                continue
+            cnt = self.lib.bv_kernel_count(self._ctx, k, 1 if reset else 0)
+            ms = self.lib.bv_kernel_ms(self._ctx, k, 1 if reset else 0)
+            if cnt > 0:
+                out[nm.decode()] = (float(ms), int(cnt))
+        return out
 
-    def family_launches(self, family: int) -> float:
-        return float(self.lib.bv_family_launches(self._ctx, family))
+    def timer_mark(self, which: int):
+        self._check(self.lib.bv_timer_mark(self._ctx, which))
+
+    def timer_elapsed_ms(self) -> float:
+        return float(self.lib.bv_timer_elapsed_ms(self._ctx))
 
 
 class DeviceBuffer:

@@ -1,0 +1,123 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol include/b200vmaf.h
+declares (no compute calls without a GPU); model loading and SVR known answers; host logic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pqa2_b200 import _lib as L
+from pqa2_b200 import engine, model as M, report
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    hdr = open(os.path.join(ROOT, "include", "b200vmaf.h")).read()
+    declared = set(re.findall(r"\b(bv_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"bv_ctx", "bv_model"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in b200vmaf.h but not exported"
+    assert set(L.EXPORTS) <= declared
+    assert lib.bv_abi_version() == 1
+    assert lib.bv_sizeof_frame_features() == C.sizeof(L.BvFrameFeatures)
+
+
+def test_no_cpu_fallback_without_device():
+    lib = L.load()
+    if lib.bv_device_count() > 0:
+        pytest.skip("a GPU is present")
+    from pqa2_b200.extractor import BvError, FeatureExtractor
+    with pytest.raises(BvError) as e:
+        FeatureExtractor(320, 240)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_bad_arguments_rejected_before_touching_cuda():
+    lib = L.load()
+    assert not lib.bv_create(0, 8, 8, 8, 420, L.FEAT_VMAF_INT, None)
+    assert b"width/height" in lib.bv_last_error(None)
+    assert not lib.bv_create(0, 640, 480, 9, 420, L.FEAT_VMAF_INT, None)
+    assert not lib.bv_create(0, 640, 480, 8, 411, L.FEAT_VMAF_INT, None)
+    assert not lib.bv_create(0, 640, 480, 8, 420, 0, None)
+
+
+# ---- SVR pins computed from the reference's own model files ----
+@pytest.mark.parametrize("name,feat,expect,clip", [
+    ("vmaf_v0.6.1", [1, 0, 1, 1, 1, 1], 97.42804264, True),
+    ("vmaf_v0.6.1", [0.9, 3.0, 0.5, 0.85, 0.92, 0.95], 72.57929533, True),
+    ("vmaf_4k_v0.6.1", [1, 0, 1, 1, 1, 1], 100.8938, False),
+    ("vmaf_4k_v0.6.1", [1, 0, 1, 1, 1, 1], 100.0, True),
+    ("vmaf_4k_v0.6.1", [0.9, 3.0, 0.5, 0.85, 0.92, 0.95], 80.20082095, True),
+    ("vmaf_b_v0.6.3", [1, 0, 1, 1, 1, 1], 97.98639, True),
+    ("vmaf_float_v0.6.1", [1, 0, 1, 1, 1, 1], 97.42804264, True),
+])
+def test_svr_known_answers(name, feat, expect, clip):
+    m = M.resolve_model(name)
+    got = m.main.predict(np.array([feat], float), disable_clip=not clip)[0]
+    assert abs(got - expect) < 5e-5 if expect != 100.0 else got == 100.0
+
+
+def test_svr_host_matches_oracle_bit_exact():
+    import oracle
+    m = M.resolve_model("vmaf_v0.6.1").main
+    rng = np.random.default_rng(0)
+    feats = rng.uniform([0.3, 0, 0.1, 0.3, 0.4, 0.5], [1.0, 20, 1, 1, 1, 1], size=(64, 6))
+    got = m.predict(feats, disable_clip=True)
+    for i in range(64):
+        assert got[i] == oracle.svr_predict(feats[i], m.slopes, m.intercepts, m.sv, m.coef, m.gamma, m.rho)
+
+
+def test_model_files():
+    names = M.available_models()
+    for n in ["vmaf_v0.6.1", "vmaf_v0.6.1neg", "vmaf_4k_v0.6.1", "vmaf_4k_v0.6.1neg", "vmaf_b_v0.6.3",
+              "vmaf_float_v0.6.1", "vmaf_float_v0.6.1neg", "vmaf_float_4k_v0.6.1", "vmaf_float_b_v0.6.3"]:
+        assert n in names
+    neg = M.resolve_model("vmaf_v0.6.1neg")
+    assert neg.vif_enhn_gain_limit == 1.0 and neg.adm_enhn_gain_limit == 1.0
+    b = M.resolve_model("vmaf_b_v0.6.3")
+    assert len(b.bootstrap) == 20
+    assert M.resolve_model("vmaf_float_v0.6.1").is_float and not M.resolve_model("vmaf_v0.6.1").is_float
+    assert M.resolve_model(None).name == "vmaf_v0.6.1"
+    assert M.resolve_model("vmaf_v0.6.1").main.metric_keys == [
+        "integer_adm2", "integer_motion2", "integer_vif_scale0", "integer_vif_scale1", "integer_vif_scale2",
+        "integer_vif_scale3"]
+    with pytest.raises(FileNotFoundError):
+        M.resolve_model("no_such_model")
+
+
+def test_libsvm_sparse_rows():
+    sv, coef, gamma, rho = M.parse_libsvm_text(
+        "svm_type nu_svr\nkernel_type rbf\ngamma 0.04\nnr_class 2\ntotal_sv 2\nrho -1.5\nSV\n"
+        "-4 1:0.5 2:0.25 4:-1.11e-16 6:2.22e-16 \n4 1:1 3:0.5 \n", 6)
+    assert sv.shape == (2, 6) and sv[0, 2] == 0 and sv[0, 4] == 0 and sv[0, 3] == -1.11e-16 and sv[1, 2] == 0.5
+    assert list(coef) == [-4, 4] and gamma == 0.04 and rho == -1.5
+
+
+def test_motion2_rule_and_shards():
+    assert engine.motion2_from_motion([0.0, 3.0, 1.0, 2.0]) == [0.0, 1.0, 1.0, 2.0]
+    assert engine.shard_ranges(10, 3) == [(0, 3), (3, 6), (6, 10)]
+    assert engine.shard_ranges(2, 8) == [(0, 1), (1, 2)]
+    r = engine.shard_ranges(3600, 8)
+    assert r[0] == (0, 450) and r[-1] == (3150, 3600) and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+def test_pooling_and_json_writer(tmp_path):
+    frames = [{"frameNum": i, "metrics": {"vmaf": v, "integer_motion2": 0.5 * i}} for i, v in enumerate([90.0, 80.0, 70.0])]
+    p = report.pooled_metrics(frames)
+    assert p["vmaf"]["min"] == 70 and p["vmaf"]["max"] == 90 and p["vmaf"]["mean"] == 80
+    assert abs(p["vmaf"]["harmonic_mean"] - (3 / (1 / 91 + 1 / 81 + 1 / 71) - 1)) < 1e-12
+    out = tmp_path / "x_vmaf.json"
+    report.write_libvmaf_json(str(out), frames, p, 123.456)
+    import json
+    d = json.loads(out.read_text())
+    assert d["frames"][1]["frameNum"] == 1 and d["frames"][1]["metrics"]["vmaf"] == 80.0
+    assert d["pooled_metrics"]["vmaf"]["mean"] == 80.0 and d["fps"] == 123.46
+    assert '"vmaf": 80.000000' in out.read_text()
+    csvp = tmp_path / "x.csv"
+    report.write_frames_csv(str(csvp), frames)
+    lines = csvp.read_text().splitlines()
+    assert lines[0] == "Frame Number,integer_motion2,vmaf" and lines[2] == "1,0.5000,80.0000"
