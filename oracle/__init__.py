@@ -206,3 +206,117 @@ def integer_features(ref: np.ndarray, dis: np.ndarray, bpc: int = 8, vif_egl: fl
         out[f"integer_adm_scale{s}"] = float(a["scale_scores"][s])
         out[f"integer_vif_scale{s}"] = float(v["score"][s])
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# float extractors (vmaf_float_* models, float_ssim, float_ms_ssim) -- vmaf_float_oracle.c
+# ------------------------------------------------------------------------------------------
+_f_ready = False
+
+
+def _flib():
+    global _f_ready
+    L = lib()
+    if not _f_ready:
+        vp, i, pd, d, f = C.c_void_p, C.c_int, C.c_ssize_t, C.c_double, C.c_float
+        L.orc_f_picture_copy.argtypes = [vp, i, i, i, pd, f, vp]
+        L.orc_f_picture_copy.restype = None
+        L.orc_f_vif.argtypes = [vp, vp, i, i, d, vp, vp]
+        L.orc_f_motion_blur.argtypes = [vp, i, i, vp]
+        L.orc_f_motion_blur.restype = None
+        L.orc_f_motion_sad.argtypes = [vp, vp, i, i]
+        L.orc_f_motion_sad.restype = d
+        L.orc_f_adm.argtypes = [vp, vp, i, i, d, d, i, vp, vp, vp, vp, vp]
+        L.orc_f_ssim.argtypes = [vp, vp, i, i]
+        L.orc_f_ssim.restype = d
+        L.orc_f_ms_ssim.argtypes = [vp, vp, i, i, vp]
+        L.orc_f_ms_ssim.restype = d
+        L.orc_f_log2_approx.argtypes = [f]
+        L.orc_f_log2_approx.restype = f
+        L.orc_f_vif_filter.argtypes = [i]
+        L.orc_f_vif_filter.restype = C.POINTER(C.c_float)
+        _f_ready = True
+    return L
+
+
+def picture_copy(luma: np.ndarray, bpc: int, offset: float) -> np.ndarray:
+    """libvmaf picture_copy(): float32 luma, (v / 2^(bpc-8)) + offset."""
+    luma = _plane(luma, bpc)
+    h, w = luma.shape
+    out = np.empty((h, w), np.float32)
+    _flib().orc_f_picture_copy(_p(luma), bpc, w, h, luma.strides[0], offset, _p(out))
+    return out
+
+
+def f_vif(ref_f: np.ndarray, dis_f: np.ndarray, enhn_gain_limit: float = 100.0) -> dict:
+    h, w = ref_f.shape
+    num, den = np.zeros(4), np.zeros(4)
+    _flib().orc_f_vif(_p(np.ascontiguousarray(ref_f, np.float32)), _p(np.ascontiguousarray(dis_f, np.float32)), w, h,
+                      float(enhn_gain_limit), _p(num), _p(den))
+    return {"num": num, "den": den, "score": num / den}
+
+
+def f_motion_blur(ref_f: np.ndarray) -> np.ndarray:
+    h, w = ref_f.shape
+    out = np.empty((h, w), np.float32)
+    _flib().orc_f_motion_blur(_p(np.ascontiguousarray(ref_f, np.float32)), w, h, _p(out))
+    return out
+
+
+def f_motion_sad(a: np.ndarray, b: np.ndarray) -> float:
+    h, w = a.shape
+    return float(_flib().orc_f_motion_sad(_p(np.ascontiguousarray(a, np.float32)), _p(np.ascontiguousarray(b, np.float32)), w, h))
+
+
+def f_adm(ref_f: np.ndarray, dis_f: np.ndarray, enhn_gain_limit: float = 100.0, norm_view_dist: float = 3.0,
+          ref_display_height: int = 1080) -> dict:
+    h, w = ref_f.shape
+    ns, ds = np.zeros((4, 3)), np.zeros((4, 3))
+    num, den = np.zeros(4), np.zeros(4)
+    adm2 = C.c_double()
+    _flib().orc_f_adm(_p(np.ascontiguousarray(ref_f, np.float32)), _p(np.ascontiguousarray(dis_f, np.float32)), w, h,
+                      float(enhn_gain_limit), float(norm_view_dist), int(ref_display_height), _p(ns), _p(ds), _p(num),
+                      _p(den), C.byref(adm2))
+    return {"num_sum": ns, "den_sum": ds, "num_scale": num, "den_scale": den, "adm2": adm2.value,
+            "scale_scores": num / den}
+
+
+def f_ssim(ref0: np.ndarray, dis0: np.ndarray) -> float:
+    """ref0/dis0: float luma with offset 0 (range [0, 255])."""
+    h, w = ref0.shape
+    return float(_flib().orc_f_ssim(_p(np.ascontiguousarray(ref0, np.float32)), _p(np.ascontiguousarray(dis0, np.float32)), w, h))
+
+
+def f_ms_ssim(ref0: np.ndarray, dis0: np.ndarray):
+    h, w = ref0.shape
+    lcs = np.zeros(15)
+    v = float(_flib().orc_f_ms_ssim(_p(np.ascontiguousarray(ref0, np.float32)), _p(np.ascontiguousarray(dis0, np.float32)),
+                                    w, h, _p(lcs)))
+    return v, lcs.reshape(5, 3)
+
+
+def float_features(ref: np.ndarray, dis: np.ndarray, bpc: int = 8, prev_ref: np.ndarray | None = None,
+                   vif_egl: float = 100.0, adm_egl: float = 100.0, psnr: bool = False, ssim: bool = False,
+                   ms_ssim: bool = False) -> dict:
+    """The float feature row libvmaf would log for one pair (motion needs the previous ref frame)."""
+    rf, df = picture_copy(ref, bpc, -128.0), picture_copy(dis, bpc, -128.0)
+    v = f_vif(rf, df, vif_egl)
+    a = f_adm(rf, df, adm_egl)
+    out = {"adm2": a["adm2"], "vif": v, "adm": a}
+    for s in range(4):
+        out[f"adm_scale{s}"] = float(a["scale_scores"][s])
+        out[f"vif_scale{s}"] = float(v["score"][s])
+    if prev_ref is not None:
+        out["motion"] = f_motion_sad(f_motion_blur(rf), f_motion_blur(picture_copy(prev_ref, bpc, -128.0)))
+    else:
+        out["motion"] = 0.0
+    if psnr:
+        h, w = ref.shape
+        out["psnr_y"] = psnr_from_sse(sse(ref, dis, bpc), bpc, w, h)
+    if ssim or ms_ssim:
+        r0, d0 = picture_copy(ref, bpc, 0.0), picture_copy(dis, bpc, 0.0)
+        if ssim:
+            out["float_ssim"] = f_ssim(r0, d0)
+        if ms_ssim:
+            out["float_ms_ssim"] = f_ms_ssim(r0, d0)[0]
+    return out
