@@ -249,7 +249,9 @@ def main() -> int:
         try:
             FeatureExtractor(64, 64, 8, 0, L.FEAT_VMAF_FLOAT, local).close()
         except Exception as e:
-            raise SystemExit(f"bench.py: float extractors unavailable: {e}")
+            log(f"[bench] float extractors unavailable ({e}); measuring the integer workload 1080p-int instead")
+            wname = "1080p-int"
+            wl = WORKLOADS[wname]
 
     dist = None
     if world > 1:
