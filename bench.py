@@ -60,7 +60,28 @@ def kernel_bytes(name: str, w: int, h: int, bps: int) -> float | None:
         "adm_scale0": 2 * px * bps + 2 * ad[0] * 2, "adm_scale1": 2 * ad[0] * 2 + 2 * ad[1] * 4,
         "adm_scale2": 2 * ad[1] * 4 + 2 * ad[2] * 4, "adm_scale3": 2 * ad[2] * 4,
         "psnr_sse_y": 2 * px * bps,
+        # float extractors: fp32 pyramids / bands / blur
+        "f_motion_blur": px * bps + px * 4, "f_motion_sad": 2 * px * 4,
+        "f_vif_stat_s0": 2 * px * bps, "f_vif_subsample_s1": 2 * px * bps + 2 * lv[1] * 4,
+        "f_vif_stat_s1": 2 * lv[1] * 4, "f_vif_subsample_s2": 2 * lv[1] * 4 + 2 * lv[2] * 4,
+        "f_vif_stat_s2": 2 * lv[2] * 4, "f_vif_subsample_s3": 2 * lv[2] * 4 + 2 * lv[3] * 4,
+        "f_vif_stat_s3": 2 * lv[3] * 4,
+        "f_adm_scale0": 2 * px * bps + 2 * ad[0] * 4, "f_adm_scale1": 2 * ad[0] * 4 + 2 * ad[1] * 4,
+        "f_adm_scale2": 2 * ad[1] * 4 + 2 * ad[2] * 4, "f_adm_scale3": 2 * ad[2] * 4,
     }
+    # float_ssim: box decimation by f = round(min(w, h) / 256), then the 11-tap maps on the small picture
+    f = max(1, int(min(w, h) / 256.0 + 0.5))
+    sp = (w // f + (w & 1)) * (h // f + (h & 1)) if f > 1 else px
+    t["ssim_decimate"] = 2 * px * bps + 2 * sp * 4
+    t["ssim_maps"] = 2 * sp * 4 if f > 1 else 2 * px * bps
+    # float_ms_ssim: 5-level pyramid (9-tap low-pass, /2), maps on every level
+    mw, mh, prev = w, h, None
+    for sc in range(5):
+        if sc > 0:
+            nw, nh = mw // 2 + (mw & 1), mh // 2 + (mh & 1)
+            t[f"ms_ssim_lpf_s{sc}"] = (2 * mw * mh * (bps if sc == 1 else 4)) + 2 * nw * nh * 4
+            mw, mh = nw, nh
+        t[f"ms_ssim_maps_s{sc}"] = 2 * mw * mh * (bps if sc == 0 else 4)
     return t.get(name)
 
 
