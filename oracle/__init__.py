@@ -49,6 +49,8 @@ def lib():
         L.orc_vif_finish.argtypes = [vp, vp, vp]
         L.orc_vif_finish.restype = None
         L.orc_vif_log2_table.restype = C.POINTER(C.c_uint16)
+        L.orc_vif_filter.argtypes = [i]
+        L.orc_vif_filter.restype = C.POINTER(C.c_uint16)
         L.orc_adm.argtypes = [vp, vp, i, i, i, pd, d, d, i, vp, vp, vp, vp, vp, vp]
         L.orc_adm.restype = i
         L.orc_adm_rfactor.argtypes = [i, d, i, vp]

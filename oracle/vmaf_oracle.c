@@ -11,9 +11,10 @@
  * integer_adm.c, integer_psnr.c, src/predict.c, src/svm.cpp) and FFmpeg libavfilter
  * (vf_psnr.c, vf_ssim.c).  Neither library nor any golden vector of theirs exists in this
  * image, so this file restates their published algorithms from the description in
- * SURVEY.md Appendix A.  What IS pinned (tests/test_oracle_*.py): SVR known answers derived
- * from the reference's own models/*.json, identical-pair / static-clip invariants, filter
- * table sums, and an independent numpy mirror (oracle/np_mirror.py).
+ * SURVEY.md Appendix A.  What IS pinned (tests/test_oracle.py, tests/test_cpu_boundary.py): SVR
+ * known answers derived from the reference's own models/*.json, identical-pair / static-clip
+ * invariants, filter table sums, monotonicity in distortion strength, agreement between the
+ * fixed-point and the fp32 restatements, and self-generated regression vectors (tests/golden/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
  * may call into this file.  The product path (pqa2_b200/) never does.

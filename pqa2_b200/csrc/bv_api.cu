@@ -269,6 +269,18 @@ void finish_frame(bv_ctx *c, const Group &g, int f, bv_frame_features &o)
             valid |= need;
         }
     }
+    if ((c->feat & BV_FEAT_FFSSIM) && spatial) {
+        // vf_ssim.c ssim_plane(): mean over the (W/4 - 1) x (H/4 - 1) overlapped 8x8 windows
+        const int np = needs_chroma(c) ? 3 : 1;
+        for (int p = 0; p < np; ++p) {
+            int pw, ph;
+            plane_dims(c, p, &pw, &ph);
+            const int W4 = pw >> 2, H4 = ph >> 2;
+            o.ffssim[p] = (W4 < 2 || H4 < 2) ? 1.0
+                : g.h_fraw[(size_t)f * BV_FRAW_WORDS + BV_FRAW_FFSSIM + p] / ((double)(H4 - 1) * (W4 - 1));
+        }
+        valid |= BV_FEAT_FFSSIM;
+    }
     if (c->fl) valid |= bv_float_finish(c->fl, g.h_fraw + (size_t)f * BV_FRAW_WORDS, g.flags[f], &o);
     o.valid_mask = valid;
 }
@@ -349,6 +361,15 @@ int launch_group(bv_ctx *c, Group &g)
     if ((c->feat & BV_FEAT_PSNR_UV) && needs_chroma(c))
         for (int p = 1; p < 3; ++p)
             bv_launch_sse(b, group_plane(g, 0, p), group_plane(g, 1, p), c->bpc, c->cw, c->ch, p, g.d_raw, L);
+    if (c->feat & BV_FEAT_FFSSIM) {
+        const int np = needs_chroma(c) ? 3 : 1;
+        for (int p = 0; p < np; ++p) {
+            int pw, ph;
+            plane_dims(c, p, &pw, &ph);
+            bv_launch_ffssim(b, group_plane(g, 0, p), group_plane(g, 1, p), c->bpc, pw, ph, p, g.d_fraw,
+                             BV_FRAW_FFSSIM + p, BV_FRAW_WORDS, L);
+        }
+    }
     if (c->fl) bv_float_launch(c->fl, b, ry, dy, g.d_fraw, L);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(g.h_raw, g.d_raw, sizeof(unsigned long long) * g.n * BV_RAW_WORDS, cudaMemcpyDeviceToHost, st));

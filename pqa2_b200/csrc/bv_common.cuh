@@ -167,6 +167,9 @@ void bv_launch_adm(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, cons
 // psnr
 void bv_launch_sse(const BvBatch &b, BvPlane ref, BvPlane dis, int bpc, int w, int h, int plane_idx,
                    unsigned long long *raw, const BvLaunch &L);
+// ffmpeg ssim filter (sum over 8x8 windows of one plane -> fraw[fraw_idx], atomically)
+void bv_launch_ffssim(const BvBatch &b, BvPlane ref, BvPlane dis, int bpc, int w, int h, int plane_idx,
+                      double *fraw, int fraw_idx, int fraw_words, const BvLaunch &L);
 // adm host-side helpers (bv_adm.cu)
 void bv_adm_rfactor(int scale, double view_dist, int display_h, float rf[3]);
 void bv_adm_make_params(int w, int h, double view_dist, int display_h, BvAdmScaleParams sp[4]);

@@ -11,7 +11,8 @@
 #define BV_FRAW_VIF 1                 // 4 scales x (num, den)
 #define BV_FRAW_ADM 9                 // 4 scales x (num h,v,d cube sums ; den h,v,d cube sums) = 24
 #define BV_FRAW_SSIM 33               // sum of the ssim map, count
-#define BV_FRAW_MS_SSIM 35            // 5 scales x (l, c, s map sums) = 15, then 5 counts -> 55
+#define BV_FRAW_MS_SSIM 35            // 5 scales x (l, c, s map sums) = 15 -> 50
+#define BV_FRAW_FFSSIM 50             // FFmpeg ssim filter: sum over 8x8 windows, planes Y, U, V
 
 struct BvFloatState;
 BvFloatState *bv_float_create(int w, int h, int bpc, unsigned feat, int batch, const bv_opts *opts);

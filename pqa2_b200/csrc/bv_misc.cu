@@ -88,7 +88,96 @@ svr_predict_kernel(const double *__restrict__ feat, int n_feat, const double *__
     if (tid == 0) out[frame] = ((s_part[0] - rho) - intercepts[0]) / slopes[0];
 }
 
+// ---- FFmpeg `ssim` filter (libavfilter/vf_ssim.c; reference app/vmaf_analyzer.py:1057-1064) ----
+// x264-style integer SSIM: 4x4 block sums (s1, s2, ss, s12), 8x8 windows at stride 4 built from four
+// blocks, ssim_end1 in float.  CTA = 32x8 windows = 33x9 blocks = 132x36 pixels staged in shared
+// memory.  Output: the sum over windows (double) -> fraw[BV_FRAW_FFSSIM + plane].
+constexpr int FS_WX = 32, FS_WY = 8, FS_BX = FS_WX + 1, FS_BY = FS_WY + 1, FS_PW = 4 * FS_BX, FS_PH = 4 * FS_BY;
+
+template <typename T, typename S>
+__global__ void __launch_bounds__(256)
+ffssim_kernel(BvBatch batch, BvPlane ref, BvPlane dis, int bpc, int w, int h, double *fraw, int fraw_idx, int fraw_words)
+{
+    __shared__ T s_a[FS_PH][FS_PW + 4];
+    __shared__ T s_b[FS_PH][FS_PW + 4];
+    __shared__ S s_blk[FS_BY][FS_BX][4];
+    __shared__ double scratch[32];
+    const int f = blockIdx.z;
+    if (batch.flags[f] & (BV_FRAME_LEAD_IN | BV_FRAME_SKIP_SPATIAL)) return;
+    const int W4 = w >> 2, H4 = h >> 2;
+    const int bx0 = blockIdx.x * FS_WX, by0 = blockIdx.y * FS_WY;
+    const uint8_t *pa = ref.p[f], *pb = dis.p[f];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < FS_PH * FS_PW; idx += 256) {
+        const int r = idx / FS_PW, c = idx - r * FS_PW;
+        const int gy = min(by0 * 4 + r, h - 1), gx = min(bx0 * 4 + c, w - 1);
+        s_a[r][c] = (T)bv_ld<T>(pa, ref.pitch, gy, gx);
+        s_b[r][c] = (T)bv_ld<T>(pb, dis.pitch, gy, gx);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < FS_BY * FS_BX; idx += 256) {
+        const int r = idx / FS_BX, c = idx - r * FS_BX;
+        S s1 = 0, s2 = 0, ss = 0, s12 = 0;
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const S p = (S)s_a[4 * r + y][4 * c + x], q = (S)s_b[4 * r + y][4 * c + x];
+                s1 += p; s2 += q; ss += p * p + q * q; s12 += p * q;
+            }
+        s_blk[r][c][0] = s1; s_blk[r][c][1] = s2; s_blk[r][c][2] = ss; s_blk[r][c][3] = s12;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    {
+        const int c = tid & 31, r = tid >> 5;
+        if (bx0 + c < W4 - 1 && by0 + r < H4 - 1) {
+            S s1 = 0, s2 = 0, ss = 0, s12 = 0;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    s1 += s_blk[r + dy][c + dx][0]; s2 += s_blk[r + dy][c + dx][1];
+                    ss += s_blk[r + dy][c + dx][2]; s12 += s_blk[r + dy][c + dx][3];
+                }
+            S c1, c2;
+            if (sizeof(T) == 1) { c1 = 416; c2 = 235963; }
+            else {
+                const int maxv = (1 << bpc) - 1;
+                c1 = (S)(long long)(.01 * .01 * maxv * maxv * 64 + .5);
+                c2 = (S)(long long)(.03 * .03 * maxv * maxv * 64 * 63 + .5);
+            }
+            const S vars = ss * 64 - s1 * s1 - s2 * s2;
+            const S covar = s12 * 64 - s1 * s2;
+            const float v = __fdiv_rn(__fmul_rn((float)(2 * s1 * s2 + c1), (float)(2 * covar + c2)),
+                                      __fmul_rn((float)(s1 * s1 + s2 * s2 + c1), (float)(vars + c2)));
+            acc = (double)v;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) scratch[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int k = 0; k < 8; ++k) s += scratch[k];
+        if (s != 0.0) atomicAdd(fraw + (size_t)f * fraw_words + fraw_idx, s);
+    }
+}
+
 }  // namespace
+
+void bv_launch_ffssim(const BvBatch &b, BvPlane ref, BvPlane dis, int bpc, int w, int h, int plane_idx,
+                      double *fraw, int fraw_idx, int fraw_words, const BvLaunch &L)
+{
+    const int W4 = w >> 2, H4 = h >> 2;
+    if (W4 < 2 || H4 < 2) return;
+    dim3 grid((W4 - 1 + FS_WX - 1) / FS_WX, (H4 - 1 + FS_WY - 1) / FS_WY, b.n);
+    bv_prof_begin(L, BVK_FFSSIM_Y + plane_idx);
+    if (bpc == 8) ffssim_kernel<uint8_t, int><<<grid, 256, 0, L.st>>>(b, ref, dis, bpc, w, h, fraw, fraw_idx, fraw_words);
+    else ffssim_kernel<uint16_t, long long><<<grid, 256, 0, L.st>>>(b, ref, dis, bpc, w, h, fraw, fraw_idx, fraw_words);
+    bv_prof_end(L, BVK_FFSSIM_Y + plane_idx);
+}
 
 void bv_launch_sse(const BvBatch &b, BvPlane ref, BvPlane dis, int bpc, int w, int h, int plane_idx,
                    unsigned long long *raw, const BvLaunch &L)

@@ -1,0 +1,158 @@
+"""CPU tests: the drop-in VMAFAnalyzer's conventions (no GPU needed for the error paths) and the
+one-process-per-GPU host logic over gloo with world_size 2 (shards, lead-in, gather, motion2 across
+the shard boundary)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from pqa2_b200 import _lib as L
+from pqa2_b200 import dist as D
+from pqa2_b200 import engine, model as M, yuvio
+from pqa2_b200.vmaf_analyzer import VMAFAnalyzer, VMAFAnalysisThread
+
+
+def test_analyzer_surface_matches_reference():
+    a = VMAFAnalyzer()
+    for name in ("set_options_from_manager", "set_options_manager", "set_output_directory", "set_test_name",
+                 "set_advanced_options", "terminate_analysis", "get_video_metadata", "analyze_videos"):
+        assert callable(getattr(a, name))
+    for sig in ("analysis_progress", "analysis_complete", "error_occurred", "status_update"):
+        s = getattr(a, sig)
+        assert hasattr(s, "connect") and hasattr(s, "emit")
+    # reference defaults (app/vmaf_analyzer.py:25-39)
+    assert (a.threads, a.pool_method, a.feature_subsample, a.psnr_enabled, a.ssim_enabled) == (4, "mean", 1, True, True)
+    assert a.enable_motion_score is False and a.enable_temporal_features is False
+
+    class Mgr:
+        def get_setting(self, k):
+            assert k == "vmaf"
+            return {"threads": 8, "feature_subsample": 3, "pool_method": "harmonic_mean", "psnr_enabled": False}
+    a.set_options_from_manager(Mgr())
+    assert (a.threads, a.feature_subsample, a.pool_method, a.psnr_enabled, a.ssim_enabled) == (8, 3, "harmonic_mean", False, True)
+    a.set_advanced_options(pool_method="min", feature_subsample=2)
+    assert a.pool_method == "min" and a.feature_subsample == 2
+    # signals are per instance
+    b = VMAFAnalyzer()
+    got = []
+    a.error_occurred.connect(got.append)
+    b.error_occurred.emit("x")
+    assert got == []
+
+
+def test_analyzer_never_raises_missing_file(tmp_path):
+    a = VMAFAnalyzer()
+    errs, done = [], []
+    a.error_occurred.connect(errs.append)
+    a.analysis_complete.connect(done.append)
+    assert a.analyze_videos(str(tmp_path / "nope_ref.y4m"), str(tmp_path / "nope_dis.y4m")) is None
+    assert errs and "Reference video not found" in errs[0] and not done
+
+
+def test_analyzer_reports_engine_errors_instead_of_raising(tmp_path):
+    """Without a GPU (this container) the engine error is emitted, not raised, and None comes back."""
+    if L.load().bv_device_count() > 0:
+        pytest.skip("a GPU is present")
+    w, h = 64, 48
+    fr = [[np.full((h, w), 100, np.uint8), np.full((h // 2, w // 2), 128, np.uint8), np.full((h // 2, w // 2), 128, np.uint8)]]
+    r, d = tmp_path / "r.y4m", tmp_path / "d.y4m"
+    yuvio.write_y4m(str(r), fr, w, h)
+    yuvio.write_y4m(str(d), fr, w, h)
+    a = VMAFAnalyzer()
+    a.set_output_directory(str(tmp_path))
+    a.set_test_name("T")
+    errs = []
+    a.error_occurred.connect(errs.append)
+    assert a.analyze_videos(str(r), str(d)) is None
+    assert errs and "CUDA" in errs[0]
+    meta = a.get_video_metadata(str(r))
+    assert meta["width"] == w and meta["height"] == h and meta["nb_frames"] == 1 and meta["pix_fmt"] == "yuv420p"
+    assert a.get_video_metadata(str(tmp_path / "missing.y4m")) is None
+
+
+def test_analysis_thread_forwards_signals(tmp_path):
+    t = VMAFAnalysisThread(str(tmp_path / "a.y4m"), str(tmp_path / "b.y4m"))
+    errs = []
+    t.error_occurred.connect(errs.append)
+    t.start()
+    t.join(30)
+    assert t.results is None and errs
+
+
+# ---- one process per GPU, world_size 2 on gloo ---------------------------------------------------
+class _FakeClip:
+    width, height, bpc, chroma, fps = 64, 48, 8, 0, 30.0
+
+    def __init__(self, n):
+        self.nb_frames = n
+
+
+def _fake_row(i, prev_seen):
+    """Stand-in for the CUDA extractors: features are functions of the frame index; motion needs the
+    previous frame (so a shard without its lead-in frame would get it wrong)."""
+    motion = 0.0 if i == 0 else abs(np.sin(i * 1.7) - np.sin((i - 1) * 1.7)) * 5
+    assert i == 0 or prev_seen, "shard started without its lead-in frame"
+    v = [0.5 + 0.4 * np.cos(i * 0.3 + s) ** 2 for s in range(4)]
+    return {"valid": L.FEAT_VMAF_INT, "raw": [0] * 64, "motion": float(motion), "vif": v,
+            "adm2": 0.8 + 0.1 * np.sin(i) ** 2, "adm_scale": [0.9] * 4, "adm_num": [1.0] * 4, "adm_den": [1.0] * 4,
+            "vif_num": v, "vif_den": [1.0] * 4, "psnr": [40.0, 0, 0], "ffssim": [0, 0, 0], "f_motion": 0.0,
+            "f_vif": [0] * 4, "f_adm2": 0.0, "f_adm_scale": [0] * 4, "float_ssim": 0.0, "float_ms_ssim": 0.0}
+
+
+def _fake_shard(src, model, opt, device, start, end, mask):
+    lead = 1 if start > 0 else 0
+    out, seen_prev = {}, False
+    for i in range(start - lead, end):
+        if i >= start:
+            out[i] = _fake_row(i, seen_prev or i == 0)
+        seen_prev = True
+    return out
+
+
+def _worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = M.resolve_model("vmaf_v0.6.1")
+        opt = engine.EngineOptions(svr_on_device=False)
+        res = D.analyze_distributed(_FakeClip(n), model, opt, shard_fn=_fake_shard)
+        t = D.max_over_ranks(10.0 + rank)
+        if rank == 0:
+            q.put(([fr["metrics"] for fr in res["frames"]], res["pooled_metrics"]["vmaf"], t))
+        else:
+            assert res is None and t == 10.0 + world - 1
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("n", [7, 2])
+def test_two_rank_gloo_matches_single_process(n):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    metrics, pooled, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert tmax == 11.0
+    # single-process truth
+    model = M.resolve_model("vmaf_v0.6.1")
+    rows = [_fake_row(i, True) for i in range(n)]
+    frames = engine.build_frames(rows, model, engine.EngineOptions(svr_on_device=False), None)
+    assert len(metrics) == n
+    for a, b in zip(metrics, frames):
+        assert a == b["metrics"]                     # bit-identical, incl. motion2 across the shard boundary
+    assert D.rank_range(7, 0, 2) == (0, 3) and D.rank_range(7, 1, 2) == (3, 7) and D.rank_range(1, 1, 2) == (1, 1)

@@ -145,3 +145,39 @@ def test_float_model_vmaf_within_north_star_tolerance():
         assert abs(fr["metrics"]["float_ssim"] - rows[i]["float_ssim"]) < 1e-6
         assert abs(fr["metrics"]["float_ms_ssim"] - rows[i]["float_ms_ssim"]) < 1e-6
         assert "vif_scale0" in fr["metrics"] and "adm2" in fr["metrics"] and "motion2" in fr["metrics"]
+
+
+def test_gpu_matches_golden_fixtures():
+    """The committed regression vectors (tests/golden, oracle outputs) straight against the kernels."""
+    import glob
+    import json
+    import os
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "oracle_*.json"))):
+        g = json.load(open(path))
+        c = g["case"]
+        w, h, bpc = c["w"], c["h"], c["bpc"]
+        ms = "float_ms_ssim" in g["frames"][0]["float"]
+        mask = L.FEAT_VMAF_INT | L.FEAT_VMAF_FLOAT | L.FEAT_PSNR_Y | L.FEAT_PSNR_UV | L.FEAT_FFSSIM | L.FEAT_FLOAT_SSIM
+        mask |= L.FEAT_FLOAT_MS_SSIM if ms else 0
+        with FeatureExtractor(w, h, bpc, 420, mask) as fx:
+            for f in range(c["n"]):
+                rp, dp = synth.frame_pair(c["seed"], f, w, h, bpc)
+                fx.submit(f, rp, dp, L.FRAME_FIRST if f == 0 else 0)
+            out = fx.fetch()
+        for f, row in enumerate(g["frames"]):
+            raw = np.array(out[f].raw[:], dtype=np.int64)
+            assert raw[L.RAW_SAD] == row["sad"]
+            assert raw[L.RAW_VIF:L.RAW_VIF + 28].reshape(4, 7).tolist() == row["vif_acc"]
+            assert raw[L.RAW_ADM_CM:L.RAW_ADM_CM + 12].reshape(4, 3).tolist() == row["adm_cm"]
+            assert raw[L.RAW_ADM_DEN:L.RAW_ADM_DEN + 12].reshape(4, 3).tolist() == row["adm_den"]
+            assert out[f].adm2 == row["adm2"]
+            assert raw[L.RAW_SSE:L.RAW_SSE + 3].tolist() == row["sse"]
+            for k in range(3):
+                assert abs(out[f].ffssim[k] - row["ffssim"][k]) < 2e-7
+            fl = row["float"]
+            assert abs(out[f].f_adm2 - fl["adm2"]) < ABS_FEAT and abs(out[f].f_motion - fl["motion"]) < ABS_FEAT
+            for s in range(4):
+                assert abs(out[f].f_vif_scale[s] - fl[f"vif_scale{s}"]) < ABS_FEAT
+            assert abs(out[f].float_ssim - fl["float_ssim"]) < 1e-6
+            if ms:
+                assert abs(out[f].float_ms_ssim - fl["float_ms_ssim"]) < 1e-6

@@ -3,6 +3,8 @@
 Every comparison is on the raw integer accumulators the kernels produce AND on the derived doubles
 (libvmaf's `integer_*` metrics).  The oracle (oracle/vmaf_oracle.c) restates libvmaf's
 integer_motion.c / integer_vif.c / integer_adm.c / integer_psnr.c."""
+import os
+
 import numpy as np
 import pytest
 
@@ -152,3 +154,64 @@ def test_device_resident_submission_matches_host_submission():
     for f in range(3):
         assert list(host[f].raw) == list(dev[f].raw)
     buf.free()
+
+
+@pytest.mark.parametrize("w,h,bpc", [(176, 144, 8), (333, 251, 8), (416, 240, 10)])
+def test_ffmpeg_ssim_filter(w, h, bpc):
+    """FFmpeg `ssim` filter (reference app/vmaf_analyzer.py:1057-1064): x264-style integer SSIM per plane.
+    Per-window values are bit-identical to the oracle; only the order of the final float sum differs."""
+    frames = [synth.frame_pair(6, f, w, h, bpc) for f in range(2)]
+    with FeatureExtractor(w, h, bpc, 420, L.FEAT_FFSSIM | L.FEAT_PSNR_Y) as fx:
+        for f, (rp, dp) in enumerate(frames):
+            fx.submit(f, rp, dp, L.FRAME_FIRST if f == 0 else 0)
+        out = fx.fetch()
+    for f, (rp, dp) in enumerate(frames):
+        assert out[f].valid_mask & L.FEAT_FFSSIM
+        for k in range(3):
+            assert abs(out[f].ffssim[k] - oracle.ffssim_plane(rp[k], dp[k], bpc)) < 2e-7
+
+
+def test_analyzer_end_to_end_on_y4m(tmp_path):
+    """The drop-in VMAFAnalyzer (reference app/vmaf_analyzer.py:242-616) on a small Y4M pair: same files,
+    same results-dict keys, per-frame metrics equal to the oracle's."""
+    import json
+    from pqa2_b200 import yuvio
+    from pqa2_b200.vmaf_analyzer import VMAFAnalyzer
+    w, h, n = 320, 180, 5
+    frames = [synth.frame_pair(12, f, w, h, 8) for f in range(n)]
+    rpath, dpath = tmp_path / "ref_320x180.y4m", tmp_path / "dis_320x180.y4m"
+    yuvio.write_y4m(str(rpath), [fr[0] for fr in frames], w, h)
+    yuvio.write_y4m(str(dpath), [fr[1] for fr in frames], w, h)
+    a = VMAFAnalyzer()
+    a.set_output_directory(str(tmp_path))
+    a.set_test_name("Clip")
+    a.set_advanced_options(pool_method="harmonic_mean")       # reference :383-386: adds psnr=1, ssim=1
+    prog, done, errs = [], [], []
+    a.analysis_progress.connect(prog.append)
+    a.analysis_complete.connect(done.append)
+    a.error_occurred.connect(errs.append)
+    res = a.analyze_videos(str(rpath), str(dpath), "vmaf_v0.6.1")
+    assert not errs and res is not None and done and done[0] is res
+    assert prog[-1] == 100 and max(prog[:-1]) <= 95
+    for k in ("vmaf_score", "psnr_score", "ssim_score", "json_path", "psnr_log", "ssim_log", "reference_video",
+              "distorted_video", "raw_results", "model", "width", "height"):
+        assert k in res
+    assert res["json_path"].endswith("_vmaf.json") and res["width"] == w and res["reference_video"] == rpath.name
+    log = json.load(open(res["json_path"]))
+    assert len(log["frames"]) == n and set(log) >= {"version", "fps", "frames", "pooled_metrics", "aggregate_metrics"}
+    rows = _oracle_rows(frames, w, h, 8)
+    motion = [r["motion"] for r in rows]
+    motion2 = [min(motion[i], motion[i + 1]) if i + 1 < n else motion[i] for i in range(n)]
+    for i, fr in enumerate(log["frames"]):
+        m = fr["metrics"]
+        assert fr["frameNum"] == i
+        assert abs(m["integer_adm2"] - rows[i]["adm"]["adm2"]) < 5e-7            # %.6f in the log
+        assert abs(m["integer_motion2"] - motion2[i]) < 5e-7
+        for s in range(4):
+            assert abs(m[f"integer_vif_scale{s}"] - rows[i]["vif"]["score"][s]) < 5e-7
+        assert "psnr_y" in m and "float_ssim" in m and 0 <= m["vmaf"] <= 100
+    assert abs(res["vmaf_score"] - log["pooled_metrics"]["vmaf"]["mean"]) < 1e-6
+    assert os.path.exists(res["psnr_log"]) and os.path.exists(res["ssim_log"])
+    first = open(res["psnr_log"]).readline()
+    assert first.startswith("n:1 mse_avg:") and "psnr_y:" in first
+    assert open(res["ssim_log"]).readline().startswith("n:1 Y:")

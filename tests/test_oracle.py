@@ -1,0 +1,96 @@
+"""CPU tests of the oracle itself (no GPU): regression vectors under tests/golden/ (made by
+tools/make_golden.py from the oracle -- the reference ships no golden vectors), and the pins
+SURVEY.md §8c lists: filter tables, identical-pair and static-clip invariants, monotonicity."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from pqa2_b200 import synth
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "oracle_*.json")))
+
+
+def _crc(a):
+    return int(np.bitwise_xor.reduce(a.astype(np.uint32).ravel() * np.uint32(2654435761)))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_matches_golden(path):
+    g = json.load(open(path))
+    c = g["case"]
+    w, h, bpc = c["w"], c["h"], c["bpc"]
+    prev_blur, prev_ref = None, None
+    for f, row in enumerate(g["frames"]):
+        rp, dp = synth.frame_pair(c["seed"], f, w, h, bpc)
+        assert [_crc(rp[0]), _crc(dp[0])] == row["luma_crc"], "synthetic generator changed"
+        blur = oracle.motion_blur(rp[0], bpc)
+        sad = 0 if prev_blur is None else oracle.motion_sad(blur, prev_blur)
+        prev_blur = blur
+        assert sad == row["sad"]
+        v, a = oracle.vif(rp[0], dp[0], bpc), oracle.adm(rp[0], dp[0], bpc)
+        assert v["acc"].tolist() == row["vif_acc"]
+        assert a["cm"].tolist() == row["adm_cm"]
+        assert [[int(x) for x in r] for r in a["den"]] == row["adm_den"]
+        assert a["adm2"] == row["adm2"]
+        assert [oracle.sse(rp[k], dp[k], bpc) for k in range(3)] == row["sse"]
+        for k in range(3):
+            assert oracle.ffssim_plane(rp[k], dp[k], bpc) == row["ffssim"][k]
+        fl = oracle.float_features(rp[0], dp[0], bpc, prev_ref=prev_ref, psnr=True, ssim=True,
+                                   ms_ssim="float_ms_ssim" in row["float"])
+        prev_ref = rp[0]
+        for k, val in row["float"].items():
+            assert fl[k] == val, k
+
+
+def test_filter_tables():
+    for s, n in enumerate((17, 9, 5, 3)):
+        assert int(np.ctypeslib.as_array(oracle.lib().orc_vif_filter(s), (17,))[:n].sum()) == 65536
+    t = np.ctypeslib.as_array(oracle.lib().orc_vif_log2_table(), (65536,))
+    assert t[32768] == 30720 and t[65535] == 32768
+    L = oracle._flib()
+    for s, n in enumerate((17, 9, 5, 3)):
+        f = np.ctypeslib.as_array(L.orc_f_vif_filter(s), (n,))
+        assert abs(float(f.sum()) - 1.0) < 1e-6 and np.allclose(f, f[::-1])
+    assert abs(L.orc_f_log2_approx(8.0) - 3.0) < 1e-6 and abs(L.orc_f_log2_approx(1.5) - np.log2(1.5)) < 1e-4
+
+
+@pytest.mark.parametrize("bpc", [8, 10])
+def test_identical_pair_and_static_clip(bpc):
+    w, h = 192, 128
+    rp, _ = synth.frame_pair(2, 0, w, h, bpc)
+    v, a = oracle.vif(rp[0], rp[0], bpc), oracle.adm(rp[0], rp[0], bpc)
+    assert all(abs(s - 1.0) < 1e-4 for s in v["score"]) and abs(a["adm2"] - 1.0) < 1e-4
+    assert oracle.psnr_from_sse(oracle.sse(rp[0], rp[0], bpc), bpc, w, h) == 6.0 * bpc + 12.0
+    b = oracle.motion_blur(rp[0], bpc)
+    assert oracle.motion_sad(b, b) == 0 and oracle.motion_score(0, w, h) == 0.0
+    fl = oracle.float_features(rp[0], rp[0], bpc, prev_ref=rp[0], ssim=True)
+    assert fl["adm2"] == 1.0 and fl["motion"] == 0.0 and abs(fl["float_ssim"] - 1.0) < 1e-12
+    assert all(abs(fl[f"vif_scale{s}"] - 1.0) < 1e-5 for s in range(4))
+    assert oracle.ffssim_plane(rp[0], rp[0], bpc) == pytest.approx(1.0, abs=1e-6)
+
+
+def test_monotone_in_distortion_strength():
+    w, h = 256, 144
+    prev = None
+    for strength in (1, 2, 3):
+        rp, dp = synth.frame_pair(4, 1, w, h, 8, chroma=False, strength=strength)
+        v, a = oracle.vif(rp[0], dp[0], 8), oracle.adm(rp[0], dp[0], 8)
+        fl = oracle.float_features(rp[0], dp[0], 8)
+        cur = (v["score"][0], a["adm2"], fl["vif_scale0"], fl["adm2"])
+        if prev is not None:
+            assert all(c < p for c, p in zip(cur, prev)), (strength, cur, prev)
+        prev = cur
+
+
+def test_integer_and_float_extractors_agree_roughly():
+    """Two independent restatements (fixed-point and fp32) of the same features."""
+    w, h = 320, 192
+    rp, dp = synth.frame_pair(6, 0, w, h, 8, chroma=False)
+    v, a, fl = oracle.vif(rp[0], dp[0], 8), oracle.adm(rp[0], dp[0], 8), oracle.float_features(rp[0], dp[0], 8)
+    for s in range(4):
+        assert abs(v["score"][s] - fl[f"vif_scale{s}"]) < 5e-3
+    assert abs(a["adm2"] - fl["adm2"]) < 5e-3
