@@ -14,13 +14,15 @@
 #include "bv_common.cuh"
 #include "../../include/b200vmaf.h"
 #include <math.h>
+#include <type_traits>
 
 namespace {
 
 constexpr int AT_W = 64, AT_H = 16, AT_THREADS = 256;
 constexpr int AP_W = AT_W + 2, AP_H = AT_H + 2;          // band positions incl. the contrast-masking halo
-constexpr int AN_C = 2 * AT_W + 6, AN_R = 2 * AT_H + 6;  // staged input samples
-constexpr int AN_P = AN_C + 2;                           // shared-memory pitch (elements)
+constexpr int AN_C = 2 * AT_W + 8, AN_R = 2 * AT_H + 6;  // staged input samples (columns start at 2*tx0 - 4: 4-sample aligned)
+constexpr int AN_P = AN_C;                               // shared-memory pitch (elements)
+constexpr int AN_G = AN_C / 4;                           // 4-sample groups per staged row
 constexpr int A_RING = 2 * AP_W + 2 * AT_H;              // halo-only positions
 
 __constant__ int c_dwt_lo[4] = { 15826, 27411, 7345, -4240 };
@@ -38,6 +40,7 @@ struct AdmArgs {
     float cos_1deg_sq;
     unsigned long long *rows;        // [frame][rows_frame_stride]; this scale at + rows_offset: [row][6]
     size_t rows_frame_stride, rows_offset;
+    int vec_ok;                      // planes aligned for 4-sample vector loads
 };
 
 template <int SCALE> struct AdmTypes;
@@ -124,13 +127,31 @@ __device__ __forceinline__ void adm_decouple_csf(const int (&o)[3], const int (&
     ccsum = (int)cc_acc;
 }
 
+template <typename Stage> struct StageStore;
+template <> struct StageStore<uint16_t> {
+    static __device__ __forceinline__ void st(uint16_t *p, const unsigned (&u)[4]) { *reinterpret_cast<uint2 *>(p) = make_uint2(u[0] | (u[1] << 16), u[2] | (u[3] << 16)); }
+};
+template <> struct StageStore<int16_t> {
+    static __device__ __forceinline__ void st(int16_t *p, const int (&u)[4])
+    {
+        *reinterpret_cast<uint2 *>(p) = make_uint2(((unsigned)u[0] & 0xffffu) | ((unsigned)u[1] << 16), ((unsigned)u[2] & 0xffffu) | ((unsigned)u[3] << 16));
+    }
+};
+template <> struct StageStore<int32_t> {
+    static __device__ __forceinline__ void st(int32_t *p, const int (&u)[4]) { *reinterpret_cast<int4 *>(p) = make_int4(u[0], u[1], u[2], u[3]); }
+};
+
+// Persistent CTAs over (frame, tile) work items with register prefetch of the next tile's samples.
 template <int SCALE, typename TIn>
-__global__ void __launch_bounds__(AT_THREADS)
-adm_scale_kernel(BvBatch batch, AdmArgs a)
+__global__ void __launch_bounds__(AT_THREADS, 2)
+adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int total_tiles)
 {
     using Stage = typename AdmTypes<SCALE>::Stage;
     using VT = typename AdmTypes<SCALE>::V;
     using Out = typename AdmTypes<SCALE>::Out;
+    using V4 = typename Px4<TIn>::V;
+    using Raw = typename std::conditional<std::is_signed<TIn>::value, int, unsigned>::type;
+    constexpr int NGRP = AN_R * AN_G, NPF = (NGRP + AT_THREADS - 1) / AT_THREADS;
 
     extern __shared__ __align__(16) unsigned char smem[];
     VT *s_v = reinterpret_cast<VT *>(smem);                                          // [AP_H][AN_P]
@@ -140,28 +161,56 @@ adm_scale_kernel(BvBatch batch, AdmArgs a)
     unsigned long long *s_row = reinterpret_cast<unsigned long long *>(s_cc + AT_H * AT_W);   // [AT_H][6]
     Stage *s_in = reinterpret_cast<Stage *>(s_row + AT_H * 6);                       // [2][AN_R][AN_P]
 
-    const int f = blockIdx.z;
-    if (batch.flags[f] & (BV_FRAME_LEAD_IN | BV_FRAME_SKIP_SPATIAL)) return;
-
     const int in_w = a.sp.in_w, in_h = a.sp.in_h, ow = a.sp.w, oh = a.sp.h;
-    const int tx0 = blockIdx.x * AT_W, ty0 = blockIdx.y * AT_H;
-    const int cx0 = 2 * tx0 - 3, ry0 = 2 * ty0 - 3;
     const int tid = threadIdx.x;
+    V4 pre_r[NPF], pre_d[NPF];
+
+    auto prefetch = [&](int t) {
+        const int f = t / tiles_per_frame, rem = t - f * tiles_per_frame;
+        if (batch.flags[f] & (BV_FRAME_LEAD_IN | BV_FRAME_SKIP_SPATIAL)) return;
+        const int by = rem / tiles_x, bx = rem - by * tiles_x;
+        const int cx0 = 2 * bx * AT_W - 4, ry0 = 2 * by * AT_H - 3;
+        const uint8_t *pr = a.ref.p[f], *pd = a.dis.p[f];
+#pragma unroll
+        for (int k = 0; k < NPF; ++k) {
+            const int g = tid + k * AT_THREADS;
+            if (g < NGRP) {
+                const int r = g / AN_G, gc = g - r * AN_G;
+                const int gy = bv_mirror(clampi(ry0 + r, -(in_h - 1), 2 * in_h - 1), in_h);
+                pre_r[k] = load_px4<TIn>(pr + (size_t)gy * a.ref.pitch, cx0 + 4 * gc, in_w, 2 * in_w - 1, a.vec_ok);
+                pre_d[k] = load_px4<TIn>(pd + (size_t)gy * a.dis.pitch, cx0 + 4 * gc, in_w, 2 * in_w - 1, a.vec_ok);
+            }
+        }
+    };
+
+    int t = blockIdx.x;
+    if (t < total_tiles) prefetch(t);
+    for (; t < total_tiles; t += gridDim.x) {
+    const int f = t / tiles_per_frame, rem = t - f * tiles_per_frame;
+    const bool skip = batch.flags[f] & (BV_FRAME_LEAD_IN | BV_FRAME_SKIP_SPATIAL);          // CTA-uniform
+    const int tx0 = (rem % tiles_x) * AT_W, ty0 = (rem / tiles_x) * AT_H;
+    const int cx0 = 2 * tx0 - 4, ry0 = 2 * ty0 - 3;
 
     if (tid < AT_H * 6) s_row[tid] = 0ull;
 
-    // ---- phase A: stage the input tile of both pictures (MIRROR resolved, far overhang clamped) ----
-    {
-        const uint8_t *pr = a.ref.p[f], *pd = a.dis.p[f];
-        for (int idx = tid; idx < AN_R * AN_C; idx += AT_THREADS) {
-            const int r = idx / AN_C, c = idx - r * AN_C;
-            const int gy = bv_mirror(clampi(ry0 + r, -(in_h - 1), 2 * in_h - 1), in_h);
-            const int gx = bv_mirror(clampi(cx0 + c, -(in_w - 1), 2 * in_w - 1), in_w);
-            s_in[r * AN_P + c] = (Stage)__ldg(reinterpret_cast<const TIn *>(pr + (size_t)gy * a.ref.pitch) + gx);
-            s_in[(AN_R + r) * AN_P + c] = (Stage)__ldg(reinterpret_cast<const TIn *>(pd + (size_t)gy * a.dis.pitch) + gx);
+    // ---- phase A: registers -> shared (MIRROR was resolved by the loads) ----
+    if (!skip) {
+#pragma unroll
+        for (int k = 0; k < NPF; ++k) {
+            const int g = tid + k * AT_THREADS;
+            if (g < NGRP) {
+                const int r = g / AN_G, gc = g - r * AN_G;
+                Raw ur[4], ud[4];
+                Px4<TIn>::raw(pre_r[k], ur);
+                Px4<TIn>::raw(pre_d[k], ud);
+                StageStore<Stage>::st(s_in + r * AN_P + 4 * gc, ur);
+                StageStore<Stage>::st(s_in + (AN_R + r) * AN_P + 4 * gc, ud);
+            }
         }
     }
     __syncthreads();
+    if (t + (int)gridDim.x < total_tiles) prefetch(t + gridDim.x);
+    if (skip) continue;
 
     // ---- phase B: vertical DWT pass: lo/hi of ref and dis for every band row of the halo tile ----
     for (int idx = tid; idx < AP_H * AN_C; idx += AT_THREADS) {
@@ -339,6 +388,7 @@ adm_scale_kernel(BvBatch batch, AdmArgs a)
         if (s && ty0 + rr < oh)
             atomicAdd(a.rows + (size_t)f * a.rows_frame_stride + a.rows_offset + (size_t)(ty0 + rr) * 6 + k, s);
     }
+    }   // tile loop
 }
 
 template <int SCALE> size_t adm_smem()
@@ -386,8 +436,16 @@ void launch_scale(const BvBatch &b, const AdmArgs &a, cudaStream_t st)
         cudaFuncSetAttribute(adm_scale_kernel<SCALE, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    dim3 grid((a.sp.w + AT_W - 1) / AT_W, (a.sp.h + AT_H - 1) / AT_H, b.n);
-    adm_scale_kernel<SCALE, TIn><<<grid, AT_THREADS, smem, st>>>(b, a);
+    const int tiles_x = (a.sp.w + AT_W - 1) / AT_W, tiles_per_frame = tiles_x * ((a.sp.h + AT_H - 1) / AT_H);
+    const int total = tiles_per_frame * b.n;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int ctas = total < 2 * sms ? total : 2 * sms;
+    adm_scale_kernel<SCALE, TIn><<<ctas, AT_THREADS, smem, st>>>(b, a, tiles_x, tiles_per_frame, total);
 }
 
 float dwt_quant_step(int lambda, int theta, double view_dist, int display_h)
@@ -519,6 +577,12 @@ void bv_launch_adm(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, cons
         a.a_dis = s < 3 ? static_cast<uint8_t *>(ab.bands[s]) + (size_t)BV_MAX_BATCH * ab.band_plane_elems[s] * esz : nullptr;
         a.sp = sp[s]; a.bpc = bpc; a.div_lookup = ab.div_lookup; a.egl = egl; a.cos_1deg_sq = cos_1deg_sq;
         a.rows = ab.rows; a.rows_frame_stride = ab.rows_frame_stride; a.rows_offset = ab.rows_scale_offset[s];
+        {
+            const size_t in_sz = s == 0 ? (bpc == 8 ? 1 : 2) : (s == 1 ? 2 : 4);
+            size_t bits = cr.pitch | cd.pitch;
+            for (int k = 0; k < b.n; ++k) bits |= (size_t)cr.p[k] | (size_t)cd.p[k];
+            a.vec_ok = (bits & (4 * in_sz - 1)) == 0;
+        }
         bv_prof_begin(L, BVK_ADM_S0 + s);
         switch (s) {
         case 0:

@@ -74,6 +74,80 @@ __device__ __forceinline__ unsigned bv_ld(const uint8_t *base, size_t pitch, int
     return (unsigned)__ldg(reinterpret_cast<const T *>(base + (size_t)i * pitch) + j);
 }
 
+// ---- 4-pixel groups: the unit of the tile prefetch ---------------------------------------------
+template <typename T> struct Px4;
+template <> struct Px4<uint8_t> {
+    using V = unsigned;
+    static __device__ __forceinline__ V pack(unsigned a, unsigned b, unsigned c, unsigned d) { return a | (b << 8) | (c << 16) | (d << 24); }
+    static __device__ __forceinline__ void unpack(V v, float s, float o, float (&f)[4])
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = fmaf((float)((v >> (8 * k)) & 0xffu), s, o);
+    }
+    static __device__ __forceinline__ void raw(V v, unsigned (&u)[4])
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = (v >> (8 * k)) & 0xffu;
+    }
+};
+template <> struct Px4<uint16_t> {
+    using V = uint2;
+    static __device__ __forceinline__ V pack(unsigned a, unsigned b, unsigned c, unsigned d) { return make_uint2(a | (b << 16), c | (d << 16)); }
+    static __device__ __forceinline__ void unpack(V v, float s, float o, float (&f)[4])
+    {
+        f[0] = fmaf((float)(v.x & 0xffffu), s, o); f[1] = fmaf((float)(v.x >> 16), s, o);
+        f[2] = fmaf((float)(v.y & 0xffffu), s, o); f[3] = fmaf((float)(v.y >> 16), s, o);
+    }
+    static __device__ __forceinline__ void raw(V v, unsigned (&u)[4])
+    {
+        u[0] = v.x & 0xffffu; u[1] = v.x >> 16; u[2] = v.y & 0xffffu; u[3] = v.y >> 16;
+    }
+};
+template <> struct Px4<float> {
+    using V = float4;
+    static __device__ __forceinline__ V pack(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
+    static __device__ __forceinline__ void unpack(V v, float s, float o, float (&f)[4])
+    {
+        f[0] = fmaf(v.x, s, o); f[1] = fmaf(v.y, s, o); f[2] = fmaf(v.z, s, o); f[3] = fmaf(v.w, s, o);
+    }
+};
+
+template <> struct Px4<int16_t> {
+    using V = uint2;
+    static __device__ __forceinline__ V pack(int a, int b, int c, int d)
+    {
+        return make_uint2(((unsigned)a & 0xffffu) | ((unsigned)b << 16), ((unsigned)c & 0xffffu) | ((unsigned)d << 16));
+    }
+    static __device__ __forceinline__ void raw(V v, int (&u)[4])
+    {
+        u[0] = (int)(short)(v.x & 0xffffu); u[1] = (int)v.x >> 16; u[2] = (int)(short)(v.y & 0xffffu); u[3] = (int)v.y >> 16;
+    }
+};
+template <> struct Px4<int32_t> {
+    using V = int4;
+    static __device__ __forceinline__ V pack(int a, int b, int c, int d) { return make_int4(a, b, c, d); }
+    static __device__ __forceinline__ void raw(V v, int (&u)[4]) { u[0] = v.x; u[1] = v.y; u[2] = v.z; u[3] = v.w; }
+};
+
+// Loads 4 consecutive pixels of row `row` starting at column gx0 (may hang over either image edge:
+// resolved per element then, BORDER 0 = libvmaf MIRROR, 1 = reflect-101).  One vector load when the
+// group is interior and aligned.
+template <typename T, int BORDER = 0>
+__device__ __forceinline__ typename Px4<T>::V load_px4(const uint8_t *row, int gx0, int w, int far, bool vec)
+{
+    if (vec && gx0 >= 0 && gx0 + 3 < w)
+        return __ldg(reinterpret_cast<const typename Px4<T>::V *>(row + (size_t)gx0 * sizeof(T)));
+    const T *p = reinterpret_cast<const T *>(row);
+    const int lo = -(w - 1);
+    int ix[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int g = min(max(gx0 + k, lo), far);
+        ix[k] = BORDER == 0 ? bv_mirror(g, w) : bv_reflect101(g, w);
+    }
+    return Px4<T>::pack(__ldg(p + ix[0]), __ldg(p + ix[1]), __ldg(p + ix[2]), __ldg(p + ix[3]));
+}
+
 // ---- launch-parameter blocks (passed by value) --------------------------------------------------
 struct BvBatch {
     int n;                                  // frames in this launch group
