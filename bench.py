@@ -398,19 +398,26 @@ def main() -> int:
             def get(self, i, luma_only):
                 return [host_ref[i % P]], [host_dis[i % P]]
 
-        n_e2e = fps_step * max(1, min(args.steps, 8))
-        engine.analyze(PinnedClip(min(n_e2e, 2 * B)), model, opt)            # warm-up (allocations, first launches)
-        barrier()
-        t0 = time.perf_counter()
-        res = engine.analyze(PinnedClip(n_e2e), model, opt)
-        dt = time.perf_counter() - t0
+        # one engine session (contexts + pinned rings stay alive between clips, as in a sweep of many clips);
+        # a step = one engine.analyze call over fps_step host frames: H2D of every frame, kernels, D2H of the
+        # feature rows, SVR fusion and pooling -- all inside the timed region.
+        k_e2e = max(1, min(args.steps, 10))
+        with engine.Engine() as sess:
+            for _ in range(2):
+                sess.analyze(PinnedClip(fps_step), model, opt)                    # warm-up (allocations, first launches)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                res = sess.analyze(PinnedClip(fps_step), model, opt)
+            dt = time.perf_counter() - t0
         dt = max_over_ranks(dt)
-        steps_e2e = n_e2e / fps_step
+        n_e2e = fps_step * k_e2e
         e2e = {"value": n_e2e * world / dt, "unit": "frames/s",
-               "h2d_bytes_per_step": int(2 * plane * fps_step + 6 * 8 * fps_step),
-               "d2h_bytes_per_step": int((L.BV_RAW_WORDS * 8 + 64 * 8 + 8) * fps_step),
-               "frames": n_e2e, "steps": steps_e2e,
-               "timer": "host wall clock around engine.analyze (H2D, kernels, feature D2H, SVR, pooling), max over ranks",
+               "h2d_bytes_per_step": int(2 * plane * fps_step),
+               "d2h_bytes_per_step": int((L.BV_RAW_WORDS * 8 + 64 * 8) * fps_step + 8 * fps_step),
+               "frames": n_e2e, "steps": k_e2e, "ms_per_step": 1000.0 * dt / k_e2e,
+               "timer": "host wall clock around K engine.analyze calls (pinned host frames -> H2D, kernels, feature D2H, "
+                        "SVR, pooling), max over ranks",
                "pooled_vmaf_mean": res["pooled_metrics"]["vmaf"]["mean"]}
 
     if rank != 0:

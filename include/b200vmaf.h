@@ -124,6 +124,10 @@ int64_t bv_frames_done(bv_ctx *);        /* frames whose features are ready (non
  * submission order incl. lead-in frames); blocks until they are ready. */
 int  bv_fetch(bv_ctx *, int64_t first, int64_t count, bv_frame_features *out);
 int  bv_cancel(bv_ctx *);                /* thread-safe; subsequent calls fail with BV_ERR_CANCELLED */
+/* Drain, drop the stored results and the motion state, clear a cancel: the ctx is ready for the next clip of the
+ * same geometry (the reference pays a process start per clip, app/vmaf_analyzer.py:446; a batch of clips --
+ * BASELINE.json configs[4] -- reuses one ctx per GPU). */
+int  bv_reset(bv_ctx *);
 int64_t bv_kernel_launches(bv_ctx *);    /* kernels launched by this ctx so far (bench `gpu_launches`) */
 /* Per-kernel CUDA-event profiling (events on the compute stream around every launch).  Enable with
  * bv_set_profiling(ctx, 1); ids run 0 .. bv_kernel_slots()-1, bv_kernel_name(id) is NULL for unused

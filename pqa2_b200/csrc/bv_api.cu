@@ -409,12 +409,18 @@ int submit_common(bv_ctx *c, int64_t frame_index, const void *const rp[3], const
                 int pw, ph;
                 plane_dims(c, p, &pw, &ph);
                 uint8_t *dst = g->d_planes[p][clip] + (size_t)f * c->staging_frame_bytes[p];
-                CK(cudaMemcpy2DAsync(dst, c->staging_pitch[p], src[p], stride[p], (size_t)pw * sample_bytes(c->bpc),
-                                     ph, cudaMemcpyHostToDevice, c->up));
+                const size_t row_bytes = (size_t)pw * sample_bytes(c->bpc);
+                // A 2-D copy of 1080 rows of 1920 B runs the DMA engine at well under half of PCIe
+                // speed; tightly packed host planes go over as ONE linear copy into a tight device pitch
+                // (the kernels take any pitch; 16-byte row alignment only matters for the vector paths).
+                const bool tight = stride[p] == row_bytes && (row_bytes % 16) == 0;
+                const size_t dpitch = tight ? row_bytes : c->staging_pitch[p];
+                if (g->pitch_set && g->pitch[clip][p] != dpitch)
+                    return fail(c, BV_ERR_ARG, "bv_submit: plane strides must not change within a frame group");
+                if (tight) CK(cudaMemcpyAsync(dst, src[p], row_bytes * ph, cudaMemcpyHostToDevice, c->up));
+                else CK(cudaMemcpy2DAsync(dst, dpitch, src[p], stride[p], row_bytes, ph, cudaMemcpyHostToDevice, c->up));
                 g->p[f][clip][p] = dst;
-                if (g->pitch_set && g->pitch[clip][p] != c->staging_pitch[p])
-                    return fail(c, BV_ERR_ARG, "bv_submit: mixed host/device submissions in one frame group");
-                g->pitch[clip][p] = c->staging_pitch[p];
+                g->pitch[clip][p] = dpitch;
             }
         }
     } else {
@@ -586,6 +592,20 @@ int bv_flush(bv_ctx *c)
 }
 
 int64_t bv_frames_done(bv_ctx *c) { return c ? c->ready.load() : 0; }
+
+int bv_reset(bv_ctx *c)
+{
+    if (!c) return BV_ERR_ARG;
+    c->cancelled.store(0);
+    int rc = bv_flush(c);
+    if (rc) return rc;
+    c->results.clear();
+    c->submitted = 0;
+    c->ready.store(0);
+    c->blur_prev_n = 0;
+    if (c->fl) bv_float_reset(c->fl);
+    return 0;
+}
 
 int bv_fetch(bv_ctx *c, int64_t first, int64_t count, bv_frame_features *out)
 {

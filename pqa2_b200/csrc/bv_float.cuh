@@ -17,6 +17,7 @@
 struct BvFloatState;
 BvFloatState *bv_float_create(int w, int h, int bpc, unsigned feat, int batch, const bv_opts *opts);
 void bv_float_destroy(BvFloatState *);
+void bv_float_reset(BvFloatState *);            // forget the motion state (next clip)
 void bv_float_launch(BvFloatState *, const BvBatch &b, BvPlane ref_y, BvPlane dis_y, double *d_fraw,
                      const BvLaunch &L);
 const char *bv_float_kernel_name(int id);     // ids >= BVK_F_FIRST

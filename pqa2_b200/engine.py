@@ -135,59 +135,114 @@ class _Cancelled(Exception):
 
 
 def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: int, start: int, end: int,
-               mask: int, rows: list, progress, cancel: threading.Event, errors: list, ctx_holder: list):
+               mask: int, rows: list, progress, cancel: threading.Event, errors: list, ctx_holder: list,
+               session: "Engine | None" = None):
     handle = None
+    fx = None
     try:
         handle = src.open()
         luma_only = not (mask & (L.FEAT_PSNR_UV | L.FEAT_FFSSIM)) or src.chroma in (0, 400)
         shapes = _plane_shapes(src)[: 1 if luma_only else 3]
         dtype = np.uint8 if src.bpc == 8 else np.uint16
-        fx = FeatureExtractor(src.width, src.height, src.bpc, src.chroma if not luma_only else 0, mask, device,
-                              vif_enhn_gain_limit=model.vif_enhn_gain_limit,
-                              adm_enhn_gain_limit=model.adm_enhn_gain_limit, batch_frames=opt.batch_frames)
+        key = (device, src.width, src.height, src.bpc, src.chroma if not luma_only else 0, mask,
+               model.vif_enhn_gain_limit, model.adm_enhn_gain_limit, opt.batch_frames)
+        fx = session._extractor(key) if session is not None else None
+        if fx is None:
+            fx = FeatureExtractor(src.width, src.height, src.bpc, src.chroma if not luma_only else 0, mask, device,
+                                  vif_enhn_gain_limit=model.vif_enhn_gain_limit,
+                                  adm_enhn_gain_limit=model.adm_enhn_gain_limit, batch_frames=opt.batch_frames)
+            if session is not None:
+                session._keep_extractor(key, fx)
+        else:
+            fx.reset()
         ctx_holder.append(fx)
-        with fx:
-            B = opt.batch_frames or L.BV_MAX_BATCH
-            zero_copy = bool(getattr(handle, "zero_copy", False))
-            ring = [] if zero_copy else [([pinned_empty(s, dtype) for s in shapes],
-                                          [pinned_empty(s, dtype) for s in shapes]) for _ in range(2 * B)]
-            lead = 1 if start > 0 else 0
-            ordinal = 0
-            for i in range(start - lead, end):
-                if cancel.is_set():
-                    fx.cancel()
-                    raise _Cancelled()
-                if zero_copy:
-                    rp, dp = handle.get(i, luma_only)     # caller-owned (pinned) planes, valid until we return
-                else:
-                    if ordinal and ordinal % B == 0:
-                        fx.wait_uploads()       # the half of the ring we are about to overwrite is free again
-                    rp, dp = ring[ordinal % len(ring)]
-                    handle.read_into(i, rp, dp, luma_only)
-                flags = 0
-                if i < start:
-                    flags |= L.FRAME_LEAD_IN
-                if ordinal == 0 and i == 0:
-                    flags |= L.FRAME_FIRST
-                if ordinal == 0 and i > 0 and not lead:
-                    flags |= L.FRAME_FIRST
-                if opt.n_subsample > 1 and i % opt.n_subsample != 0:
-                    flags |= L.FRAME_SKIP_SPATIAL
-                fx.submit(i, rp, dp, flags)
-                ordinal += 1
-                if progress:
-                    progress(1)
-            fx.flush()
-            out = fx.fetch(0, ordinal)
-            for k in range(lead, ordinal):
-                rows[out[k].frame_index] = _copy_features(out[k])
+        B = opt.batch_frames or L.BV_MAX_BATCH
+        zero_copy = bool(getattr(handle, "zero_copy", False))
+        ring = None
+        if not zero_copy:
+            ring = session._ring(key, shapes, dtype, 2 * B) if session is not None else \
+                [([pinned_empty(s, dtype) for s in shapes], [pinned_empty(s, dtype) for s in shapes]) for _ in range(2 * B)]
+        lead = 1 if start > 0 else 0
+        ordinal = 0
+        for i in range(start - lead, end):
+            if cancel.is_set():
+                fx.cancel()
+                raise _Cancelled()
+            if zero_copy:
+                rp, dp = handle.get(i, luma_only)     # caller-owned (pinned) planes, valid until we return
+            else:
+                if ordinal and ordinal % B == 0:
+                    fx.wait_uploads()       # the half of the ring we are about to overwrite is free again
+                rp, dp = ring[ordinal % len(ring)]
+                handle.read_into(i, rp, dp, luma_only)
+            flags = 0
+            if i < start:
+                flags |= L.FRAME_LEAD_IN
+            if ordinal == 0:
+                flags |= L.FRAME_FIRST      # nothing precedes the first frame this context sees
+            if opt.n_subsample > 1 and i % opt.n_subsample != 0:
+                flags |= L.FRAME_SKIP_SPATIAL
+            fx.submit(i, rp, dp, flags)
+            ordinal += 1
+            if progress:
+                progress(1)
+        fx.flush()
+        out = fx.fetch(0, ordinal)
+        for k in range(lead, ordinal):
+            rows[out[k].frame_index] = _copy_features(out[k])
     except _Cancelled:
         errors.append(("cancelled", None))
     except Exception as e:            # surfaced by analyze(): the caller decides how to report
         errors.append(("error", e))
     finally:
+        if fx is not None and session is None:
+            fx.close()
         if handle is not None and handle is not src:
             handle.close()
+
+
+class Engine:
+    """A session that keeps one CUDA context (and one pinned staging ring) per (device, geometry, features)
+    alive between clips.  The reference pays an ffmpeg process start per clip (app/vmaf_analyzer.py:446);
+    a sweep of many clips (BASELINE.json configs[4]) reuses the contexts instead of re-allocating
+    ~0.6 GB of device buffers each time."""
+
+    def __init__(self):
+        self._fx = {}
+        self._rings = {}
+        self._lock = threading.Lock()
+
+    def _extractor(self, key):
+        with self._lock:
+            return self._fx.get(key)
+
+    def _keep_extractor(self, key, fx):
+        with self._lock:
+            self._fx[key] = fx
+
+    def _ring(self, key, shapes, dtype, n):
+        with self._lock:
+            r = self._rings.get(key)
+            if r is None:
+                r = self._rings[key] = [([pinned_empty(s, dtype) for s in shapes], [pinned_empty(s, dtype) for s in shapes])
+                                        for _ in range(n)]
+            return r
+
+    def analyze(self, src, model, opt=None, progress_cb=None, cancel=None, frame_range=None):
+        return analyze(src, model, opt, progress_cb, cancel, frame_range, session=self)
+
+    def close(self):
+        with self._lock:
+            for fx in self._fx.values():
+                fx.close()
+            self._fx.clear()
+            self._rings.clear()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def _copy_features(f) -> dict:
@@ -314,7 +369,8 @@ def _bootstrap_metrics(model: VmafModel, scores: np.ndarray, opt: EngineOptions)
 
 
 def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None, progress_cb=None,
-            cancel: threading.Event | None = None, frame_range: tuple | None = None) -> dict:
+            cancel: threading.Event | None = None, frame_range: tuple | None = None,
+            session: "Engine | None" = None) -> dict:
     """Scores a clip; returns the libvmaf log as a dict plus ``rows`` (raw per-frame features).
 
     Raises on engine errors; returns ``None`` if cancelled."""
@@ -346,7 +402,7 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
         if b <= a:
             continue
         th = threading.Thread(target=_run_shard, args=(src, model, opt, dev, a, b, mask, rows, progress, cancel,
-                                                       errors, holders), daemon=True)
+                                                       errors, holders, session), daemon=True)
         th.start()
         threads.append(th)
     for th in threads:

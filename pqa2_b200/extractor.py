@@ -115,6 +115,12 @@ class FeatureExtractor:
     def cancel(self):
         self.lib.bv_cancel(self._ctx)
 
+    def reset(self):
+        """Ready for the next clip of the same geometry (drops stored results and the motion state)."""
+        self._check(self.lib.bv_reset(self._ctx))
+        self._keep.clear()
+        self.submitted = 0
+
     # -- results -------------------------------------------------------------------------------
     def fetch(self, first: int = 0, count: int | None = None):
         if count is None:
