@@ -424,3 +424,40 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
     return {"version": report.VERSION, "fps": n / dt if dt > 0 else 0.0, "frames": frames,
             "pooled_metrics": pooled, "aggregate_metrics": {}, "rows": rows_used,
             "model": model.name, "elapsed_s": dt, "n_frames": n}
+
+
+def analyze_batch(clips: list, model: VmafModel, opt: EngineOptions | None = None, devices=None,
+                  progress_cb=None) -> list:
+    """Many clips over many GPUs (BASELINE.json configs[4]: a sweep of 64 1080p clip pairs on 8 B200).
+
+    Whole clips are the unit here -- no lead-in frames, no cross-GPU state: clip k runs on
+    ``devices[k % len(devices)]`` through that device's session (one context per GPU, reused for every
+    clip of the same geometry).  Returns one libvmaf log dict per clip, in input order; a clip that
+    fails yields ``{"error": str}`` in its slot (the reference's per-clip error convention)."""
+    opt = opt or EngineOptions()
+    devices = list(devices if devices is not None else opt.devices) or [0]
+    results: list = [None] * len(clips)
+    lock = threading.Lock()
+    done = [0]
+
+    def worker(slot: int, dev: int):
+        from dataclasses import replace
+        o = replace(opt, devices=(dev,))
+        with Engine() as sess:
+            for k in range(slot, len(clips), len(devices)):
+                try:
+                    results[k] = sess.analyze(clips[k], model, o)
+                except Exception as e:            # noqa: BLE001
+                    results[k] = {"error": str(e)}
+                if progress_cb:
+                    with lock:
+                        done[0] += 1
+                        d = done[0]
+                    progress_cb(d, len(clips))
+
+    threads = [threading.Thread(target=worker, args=(i, d), daemon=True) for i, d in enumerate(devices)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    return results

@@ -215,3 +215,64 @@ def test_analyzer_end_to_end_on_y4m(tmp_path):
     first = open(res["psnr_log"]).readline()
     assert first.startswith("n:1 mse_avg:") and "psnr_y:" in first
     assert open(res["ssim_log"]).readline().startswith("n:1 Y:")
+
+
+def test_model_variants_end_to_end():
+    """configs[3]: the NEG model (gain limits 1.0 from the model file) and the bootstrap model (21 SVRs ->
+    bagging / stddev / CI) through engine.analyze, checked against the oracle's features + the host SVR."""
+    from pqa2_b200 import engine, model as M
+    w, h, n = 480, 270, 4
+    frames = [synth.frame_pair(31, f, w, h, 8) for f in range(n)]
+    for name in ("vmaf_v0.6.1neg", "vmaf_b_v0.6.3", "vmaf_4k_v0.6.1"):
+        model = M.resolve_model(name)
+        res = engine.analyze(engine.SynthSource(w, h, 8, n, seed=31), model, engine.EngineOptions(svr_on_device=True))
+        rows = _oracle_rows(frames, w, h, 8, vif_egl=model.vif_enhn_gain_limit, adm_egl=model.adm_enhn_gain_limit)
+        motion = [r["motion"] for r in rows]
+        motion2 = engine.motion2_from_motion(motion)
+        feats = np.array([[r["adm"]["adm2"], motion2[i]] + [r["vif"]["score"][s] for s in range(4)] for i, r in enumerate(rows)])
+        want = model.main.predict(feats, False, False, device=None)
+        got = np.array([fr["metrics"]["vmaf"] for fr in res["frames"]])
+        assert np.max(np.abs(got - want)) < 1e-9, name          # integer features are bit-exact; SVR in double both ways
+        m0 = res["frames"][0]["metrics"]
+        if name.endswith("neg"):
+            assert "integer_adm2_egl_1" in m0 and "integer_vif_scale0_egl_1" in m0
+        if "_b_" in name:
+            for k in ("vmaf_bagging", "vmaf_stddev", "vmaf_ci_p95_lo", "vmaf_ci_p95_hi"):
+                assert k in m0
+            assert m0["vmaf_ci_p95_lo"] <= m0["vmaf_bagging"] <= m0["vmaf_ci_p95_hi"]
+
+
+def test_4k_10bit_single_frame_parity():
+    """configs[2] shape: 3840x2160 yuv420p10le, integer extractors, bit-exact vs the oracle (one frame)."""
+    w, h = 3840, 2160
+    frames = [synth.frame_pair(13, f, w, h, 10, chroma=False) for f in range(2)]
+    rows = _oracle_rows(frames, w, h, 10)
+    with FeatureExtractor(w, h, 10, 0, L.FEAT_VMAF_INT | L.FEAT_PSNR_Y) as fx:
+        for f, (rp, dp) in enumerate(frames):
+            fx.submit(f, rp, dp, L.FRAME_FIRST if f == 0 else 0)
+        out = fx.fetch()
+    for f in range(2):
+        _check(out[f], rows[f], w, h, 10, planes=1)
+
+
+def test_shard_invariance_and_batch_of_clips():
+    """results identical however the frames are sharded (here: 1 shard vs 3 shards with lead-in
+    frames on one GPU), and configs[4]: a batch of clips through per-device sessions == clip-by-clip."""
+    from pqa2_b200 import engine, model as M
+    w, h, n = 320, 180, 11
+    model = M.resolve_model("vmaf_v0.6.1")
+    src = engine.SynthSource(w, h, 8, n, seed=17, chroma=0)
+    one = engine.analyze(src, model, engine.EngineOptions(devices=(0,)))
+    three = engine.analyze(src, model, engine.EngineOptions(devices=(0, 0, 0)))
+    assert [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in three["frames"]]
+    fmodel = M.resolve_model("vmaf_float_v0.6.1")
+    fone = engine.analyze(src, fmodel, engine.EngineOptions(devices=(0,)))
+    fthree = engine.analyze(src, fmodel, engine.EngineOptions(devices=(0, 0, 0)))
+    assert [fr["metrics"] for fr in fone["frames"]] == [fr["metrics"] for fr in fthree["frames"]]
+    clips = [engine.SynthSource(w, h, 8, 5, seed=40 + k, chroma=0) for k in range(5)]
+    batch = engine.analyze_batch(clips, model, engine.EngineOptions(), devices=[0, 0])
+    for k, c in enumerate(clips):
+        solo = engine.analyze(c, model, engine.EngineOptions())
+        assert "error" not in batch[k]
+        assert [fr["metrics"] for fr in batch[k]["frames"]] == [fr["metrics"] for fr in solo["frames"]]
+        assert batch[k]["pooled_metrics"]["vmaf"] == solo["pooled_metrics"]["vmaf"]
