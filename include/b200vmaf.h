@@ -142,6 +142,14 @@ double bv_kernel_count(bv_ctx *, int id, int reset);
 int  bv_timer_mark(bv_ctx *, int which);
 double bv_timer_elapsed_ms(bv_ctx *);
 
+/* ---- bookend (white-frame) scan: the per-pixel step of the alignment stage that precedes the path ----
+ * Replaces the cv2 loop at app/bookend_alignment.py:997-1020 (mean / std / share of pixels above a threshold per
+ * frame) and app/reference_analyzer.py:131-141.  Frames are resident luma planes on `device`, frame f at
+ * d_luma + f * frame_stride.  out_host: [n_frames][5] = sum y, sum y^2, count(y > thr[0]), (> thr[1]), (> thr[2]).
+ * Blocking (one launch + one small D2H). */
+int  bv_luma_stats_device(int device, const void *d_luma, size_t pitch, size_t frame_stride, int n_frames,
+                          int w, int h, int bpc, const unsigned thr[3], unsigned long long *out_host);
+
 #define BV_ERR_ARG        -1
 #define BV_ERR_CUDA       -2
 #define BV_ERR_CANCELLED  -3

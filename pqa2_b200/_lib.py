@@ -70,7 +70,7 @@ EXPORTS = (
     "bv_reset",
     "bv_kernel_launches", "bv_set_profiling", "bv_kernel_slots", "bv_kernel_name", "bv_kernel_ms", "bv_kernel_count",
     "bv_timer_mark", "bv_timer_elapsed_ms",
-    "bv_model_create", "bv_model_free", "bv_predict", "bv_predict_device",
+    "bv_model_create", "bv_model_free", "bv_predict", "bv_predict_device", "bv_luma_stats_device",
 )
 
 _lib = None
@@ -137,6 +137,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.bv_model_free.restype = None
     L.bv_predict.argtypes = [vp, pd, i64, u, pd]
     L.bv_predict_device.argtypes = [vp, i, pd, i64, u, pd]
+    L.bv_luma_stats_device.argtypes = [i, vp, sz, sz, i, i, i, i, C.POINTER(C.c_uint), C.POINTER(C.c_uint64)]
     if L.bv_sizeof_frame_features() != C.sizeof(BvFrameFeatures):
         raise RuntimeError("bv_frame_features ABI mismatch between libb200vmaf.so and the ctypes binding")
     _lib = L

@@ -165,7 +165,86 @@ ffssim_kernel(BvBatch batch, BvPlane ref, BvPlane dis, int bpc, int w, int h, do
     }
 }
 
+// ---- luma statistics for bookend (white-frame) detection ------------------------------------------
+// Replaces the per-frame cv2 scan of the reference's alignment step (app/bookend_alignment.py:997-1020,
+// app/reference_analyzer.py:131-141): mean, standard deviation and the share of pixels above a
+// threshold.  Exact integer sums per frame: sum y, sum y^2, count(y > thr[k]) for 3 thresholds.
+// Pure streaming read (16-byte loads, one pass) -> HBM-bound.
+template <typename T>
+__global__ void __launch_bounds__(256)
+luma_stats_kernel(const uint8_t *base, size_t pitch, size_t frame_stride, int w, int h, uint3 thr,
+                  unsigned long long *out /* [frame][5] */)
+{
+    __shared__ long long scratch[5 * 32];
+    const int f = blockIdx.y;
+    const uint8_t *img = base + (size_t)f * frame_stride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const size_t row_bytes = (size_t)w * sizeof(T);
+    const bool vec_ok = (((uintptr_t)img | pitch) & 15) == 0;
+    unsigned long long s1 = 0, s2 = 0;
+    unsigned c0 = 0, c1 = 0, c2 = 0;
+    auto px = [&](unsigned v) {
+        s1 += v; s2 += (unsigned long long)v * v;
+        c0 += v > thr.x; c1 += v > thr.y; c2 += v > thr.z;
+    };
+    for (int row = blockIdx.x * nwarps + warp; row < h; row += gridDim.x * nwarps) {
+        const uint8_t *a = img + (size_t)row * pitch;
+        size_t done = 0;
+        if (vec_ok) {
+            const size_t nv = row_bytes / 16;
+            for (size_t v = lane; v < nv; v += 32) {
+                const uint4 x = __ldg(reinterpret_cast<const uint4 *>(a) + v);
+                const unsigned xs[4] = { x.x, x.y, x.z, x.w };
+                if (sizeof(T) == 1) {
+                    unsigned q1 = 0, q2 = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        q1 = __dp4a(xs[q], 0x01010101u, q1);
+                        q2 = __dp4a(xs[q], xs[q], q2);
+                        // per-byte compare: __vcmpgtu4 gives 0xff per true byte; popcount / 8 = number of true bytes
+                        c0 += __popc(__vcmpgtu4(xs[q], thr.x * 0x01010101u)) >> 3;
+                        c1 += __popc(__vcmpgtu4(xs[q], thr.y * 0x01010101u)) >> 3;
+                        c2 += __popc(__vcmpgtu4(xs[q], thr.z * 0x01010101u)) >> 3;
+                    }
+                    s1 += q1; s2 += q2;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { px(xs[q] & 0xffffu); px(xs[q] >> 16); }
+                }
+            }
+            done = nv * 16 / sizeof(T);
+        }
+        for (size_t j = done + lane; j < (size_t)w; j += 32) px((unsigned)reinterpret_cast<const T *>(a)[j]);
+    }
+    long long v[5] = { (long long)s1, (long long)s2, (long long)c0, (long long)c1, (long long)c2 };
+    bv_block_accumulate<5>(v, scratch, out + (size_t)f * 5);
+}
+
 }  // namespace
+
+extern "C" int bv_luma_stats_device(int device, const void *d_luma, size_t pitch, size_t frame_stride, int n_frames,
+                                    int w, int h, int bpc, const unsigned thr[3], unsigned long long *out_host)
+{
+    if (!d_luma || !thr || !out_host || n_frames <= 0 || w <= 0 || h <= 0) return -1;
+    if (cudaSetDevice(device) != cudaSuccess) return -2;
+    unsigned long long *d_out = nullptr;
+    if (cudaMalloc(&d_out, sizeof(unsigned long long) * 5 * n_frames) != cudaSuccess) return -2;
+    cudaMemset(d_out, 0, sizeof(unsigned long long) * 5 * n_frames);
+    int gx = (h + 7) / 8;
+    if (gx > 148 * 2) gx = 148 * 2;
+    // the 8-bit compare works on bytes: thresholds above 254 can never be exceeded
+    uint3 t = make_uint3(thr[0], thr[1], thr[2]);
+    if (bpc == 8) { t.x = t.x > 255 ? 255 : t.x; t.y = t.y > 255 ? 255 : t.y; t.z = t.z > 255 ? 255 : t.z; }
+    dim3 grid(gx, n_frames);
+    if (bpc == 8) luma_stats_kernel<uint8_t><<<grid, 256>>>(static_cast<const uint8_t *>(d_luma), pitch, frame_stride, w, h, t, d_out);
+    else luma_stats_kernel<uint16_t><<<grid, 256>>>(static_cast<const uint8_t *>(d_luma), pitch, frame_stride, w, h, t, d_out);
+    cudaError_t e = cudaMemcpy(out_host, d_out, sizeof(unsigned long long) * 5 * n_frames, cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    return e == cudaSuccess ? 0 : -2;
+}
+
+namespace {
+}
 
 void bv_launch_ffssim(const BvBatch &b, BvPlane ref, BvPlane dis, int bpc, int w, int h, int plane_idx,
                       double *fraw, int fraw_idx, int fraw_words, const BvLaunch &L)
