@@ -33,11 +33,11 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     "1080p-float": dict(w=1920, h=1080, bpc=8, model="vmaf_float_v0.6.1", psnr=True, ssim=True, ms_ssim=True,
-                        frames_per_step=128, pool=64, cfg="configs[1]"),
+                        frames_per_step=512, pool=64, cfg="configs[1]"),
     "1080p-int": dict(w=1920, h=1080, bpc=8, model="vmaf_v0.6.1", psnr=False, ssim=False, ms_ssim=False,
-                      frames_per_step=256, pool=64, cfg="configs[0] shape"),
+                      frames_per_step=512, pool=64, cfg="configs[0] shape"),
     "4k-int": dict(w=3840, h=2160, bpc=10, model="vmaf_4k_v0.6.1", psnr=False, ssim=False, ms_ssim=False,
-                   frames_per_step=64, pool=24, cfg="configs[2]"),
+                   frames_per_step=128, pool=24, cfg="configs[2]"),
 }
 
 # Algorithmic bytes per frame pair of each kernel at (w, h, bytes per sample): unique bytes the

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200vmaf.so")
 
 BV_RAW_WORDS = 64
-BV_MAX_BATCH = 16
+BV_MAX_BATCH = 32
 
 FEAT_MOTION = 0x001
 FEAT_VIF = 0x002

@@ -4,7 +4,7 @@
 #include <stdint.h>
 #include <stddef.h>
 
-#define BV_MAX_BATCH 16
+#define BV_MAX_BATCH 32
 
 // ---- border rules -------------------------------------------------------------------------
 // libvmaf "MIRROR" (motion, ADM DWT, CM neighbourhood): -i -> i ; n+i -> n-1-i

@@ -21,13 +21,13 @@ def rank_range(n_frames: int, rank: int, world: int, first: int = 0):
 
 
 def _default_shard_fn(src, model, opt, device, start, end, mask):
-    rows = [None] * src.nb_frames
+    rows = engine.Rows(src.nb_frames)
     errors, holders = [], []
     engine._run_shard(src, model, opt, device, start, end, mask, rows, None, threading.Event(), errors, holders)
     for kind, e in errors:
         if kind == "error":
             raise e
-    return {i: rows[i] for i in range(start, end)}
+    return ("block", start, rows.arr[start:end].copy())        # one structured array per shard (~1.3 KB/frame)
 
 
 def max_over_ranks(value: float, group=None, device=None) -> float:
@@ -57,11 +57,19 @@ def analyze_distributed(src, model, opt: engine.EngineOptions | None = None, dev
     dist.gather_object(mine, gathered, dst=0, group=group)
     if rank != 0:
         return None
-    rows = [None] * n
-    for part in gathered:
-        for i, r in part.items():
-            rows[i] = r
-    missing = [i for i, r in enumerate(rows) if r is None]
+    if all(isinstance(p, tuple) or not p for p in gathered):
+        rows = engine.Rows(n)
+        for part in gathered:
+            if part:
+                _, s0, arr = part
+                rows.put(list(range(s0, s0 + len(arr))), arr)
+        missing = [i for i in range(n) if not rows.present[i]]
+    else:                                               # dict rows (stub shard functions in the CPU tests)
+        rows = [None] * n
+        for part in gathered:
+            for i, r in part.items():
+                rows[i] = r
+        missing = [i for i, r in enumerate(rows) if r is None]
     if missing:
         raise RuntimeError(f"frames missing after the gather: {missing[:8]}...")
     frames = engine.build_frames(rows, model, opt, svr_device)

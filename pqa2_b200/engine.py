@@ -187,9 +187,12 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
             if progress:
                 progress(1)
         fx.flush()
-        out = fx.fetch(0, ordinal)
-        for k in range(lead, ordinal):
-            rows[out[k].frame_index] = _copy_features(out[k])
+        out = np.ctypeslib.as_array(fx.fetch(0, ordinal))       # structured view of the bv_frame_features records
+        if isinstance(rows, Rows):
+            rows.put(out["frame_index"][lead:ordinal], out[lead:ordinal])
+        else:
+            for k in range(lead, ordinal):
+                rows[int(out["frame_index"][k])] = RowView(out, k)
     except _Cancelled:
         errors.append(("cancelled", None))
     except Exception as e:            # surfaced by analyze(): the caller decides how to report
@@ -245,7 +248,65 @@ class Engine:
         self.close()
 
 
+ROW_DTYPE = np.dtype(L.BvFrameFeatures)        # numpy view of bv_frame_features (include/b200vmaf.h)
+
+_ROW_KEYS = {"valid": "valid_mask", "raw": "raw", "motion": "motion", "vif": "vif_scale", "adm2": "adm2",
+             "adm_scale": "adm_scale", "adm_num": "adm_num", "adm_den": "adm_den", "vif_num": "vif_num",
+             "vif_den": "vif_den", "ffssim": "ffssim", "f_motion": "f_motion", "f_vif": "f_vif_scale",
+             "f_adm2": "f_adm2", "f_adm_scale": "f_adm_scale", "float_ssim": "float_ssim",
+             "float_ms_ssim": "float_ms_ssim", "frame_index": "frame_index", "flags": "flags"}
+
+
+class RowView:
+    """One frame of a Rows block with the dict keys the host code and the callers use."""
+    __slots__ = ("_a", "_i")
+
+    def __init__(self, arr, i):
+        self._a, self._i = arr, i
+
+    def __getitem__(self, key):
+        r = self._a[self._i]
+        if key == "psnr":
+            return [float(r["psnr_y"]), float(r["psnr_cb"]), float(r["psnr_cr"])]
+        v = r[_ROW_KEYS[key]]
+        if isinstance(v, np.ndarray):
+            return v.tolist()
+        return v.item()
+
+    def keys(self):
+        return list(_ROW_KEYS) + ["psnr"]
+
+
+class Rows:
+    """Per-frame feature rows of a clip as ONE structured array (bv_frame_features records), filled shard by
+    shard.  Indexing yields dict-like RowViews; build_frames() reads whole columns."""
+
+    def __init__(self, n: int = 0, arr=None):
+        self.arr = arr if arr is not None else np.zeros(n, ROW_DTYPE)
+        self.present = np.zeros(len(self.arr), bool) if arr is None else np.ones(len(self.arr), bool)
+
+    def __len__(self):
+        return len(self.arr)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            out = Rows(arr=self.arr[i])
+            out.present = self.present[i]
+            return out
+        if not self.present[i]:
+            return None
+        return RowView(self.arr, i)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self.arr)))
+
+    def put(self, frame_indices, records):
+        self.arr[frame_indices] = records
+        self.present[frame_indices] = True
+
+
 def _copy_features(f) -> dict:
+    """Legacy dict form of one bv_frame_features record (kept for callers that build rows by hand)."""
     return {
         "valid": int(f.valid_mask), "raw": list(f.raw),
         "motion": f.motion, "vif": list(f.vif_scale), "adm2": f.adm2, "adm_scale": list(f.adm_scale),
@@ -278,8 +339,70 @@ def percentile(sorted_vals, p: float) -> float:
     return sorted_vals[lo] + (sorted_vals[hi] - sorted_vals[lo]) * (pos - lo)
 
 
-def build_frames(rows: list, model: VmafModel, opt: EngineOptions, device: int | None) -> list:
+def _build_frames_block(rows: Rows, model: VmafModel, opt: EngineOptions, device: int | None) -> list:
+    """build_frames() on a Rows block: whole columns at a time (the per-row dict path costs ~50 us/frame in
+    Python, which at several thousand frames/s is as much as the GPU work itself)."""
+    a = rows.arr
+    is_f = model.is_float
+    pre = "" if is_f else "integer_"
+    vs, as_ = _egl_suffix(model.vif_enhn_gain_limit), _egl_suffix(model.adm_enhn_gain_limit)
+    n = len(a)
+    motion = np.array(a["f_motion"] if is_f else a["motion"], np.float64)
+    if n:
+        motion[0] = 0.0
+    motion2 = motion.copy()
+    if n > 1:
+        motion2[:-1] = np.minimum(motion[:-1], motion[1:])
+    valid = a["valid_mask"]
+    scored = np.nonzero((valid & (L.FEAT_FLOAT_VIF if is_f else L.FEAT_VIF)) != 0)[0]
+    adm2 = np.asarray(a["f_adm2"] if is_f else a["adm2"])
+    adm_s = np.asarray(a["f_adm_scale"] if is_f else a["adm_scale"])
+    vif = np.asarray(a["f_vif_scale"] if is_f else a["vif_scale"])
+    base = {"adm2": adm2, "motion2": motion2, "motion": motion}
+    for k in range(4):
+        base[f"vif_scale{k}"] = vif[:, k]
+        base[f"adm_scale{k}"] = adm_s[:, k]
+    keys = model.main.metric_keys
+    feats = np.stack([base[k[len("integer_"):] if k.startswith("integer_") else k][scored] for k in keys], axis=1) \
+        if len(scored) else np.zeros((0, len(keys)))
+    cols = [(f"{pre}adm2{as_}", adm2)] + [(f"{pre}adm_scale{k}{as_}", adm_s[:, k]) for k in range(4)]
+    cols.append((f"{pre}motion2", motion2))
+    if opt.report_motion:
+        cols.append((f"{pre}motion", motion))
+    cols += [(f"{pre}vif_scale{k}{vs}", vif[:, k]) for k in range(4)]
+    opt_cols = []
+    if opt.psnr or opt.ffmpeg_psnr:
+        opt_cols.append(("psnr_y", a["psnr_y"], L.FEAT_PSNR_Y))
+    opt_cols.append(("float_ssim", a["float_ssim"], L.FEAT_FLOAT_SSIM))
+    opt_cols.append(("float_ms_ssim", a["float_ms_ssim"], L.FEAT_FLOAT_MS_SSIM))
+    names = [c[0] for c in cols]
+    table = np.stack([np.asarray(c[1], np.float64)[scored] for c in cols], axis=1).tolist() if len(scored) else []
+    extras = [(nm, np.asarray(col, np.float64)[scored].tolist(), ((valid[scored] & bit) != 0).tolist())
+              for nm, col, bit in opt_cols]
+    frames = []
+    for j, i in enumerate(scored.tolist()):
+        m = dict(zip(names, table[j]))
+        for nm, vals, ok in extras:
+            if ok[j]:
+                m[nm] = vals[j]
+        frames.append({"frameNum": i, "metrics": m})
+    if len(scored):
+        dev = device if opt.svr_on_device else None
+        vmaf = model.main.predict(feats, opt.enable_transform, opt.disable_clip, device=dev).tolist()
+        boots = None
+        if model.bootstrap:
+            boots = np.stack([b.predict(feats, False, True, device=dev) for b in model.bootstrap], axis=1)
+        for j, fr in enumerate(frames):
+            fr["metrics"]["vmaf"] = vmaf[j]
+            if boots is not None:
+                fr["metrics"].update(_bootstrap_metrics(model, boots[j], opt))
+    return frames
+
+
+def build_frames(rows, model: VmafModel, opt: EngineOptions, device: int | None) -> list:
     """Per-frame feature rows -> libvmaf 'frames' list (metric names of SURVEY.md Appendix A.8)."""
+    if isinstance(rows, Rows):
+        return _build_frames_block(rows, model, opt, device)
     is_f = model.is_float
     pre = "" if is_f else "integer_"
     vs, as_ = _egl_suffix(model.vif_enhn_gain_limit), _egl_suffix(model.adm_enhn_gain_limit)
@@ -381,7 +504,7 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
     if n <= 0:
         raise ValueError("no frames to analyze")
     mask = feature_mask(model, opt)
-    rows: list = [None] * src.nb_frames
+    rows = Rows(src.nb_frames)
     devices = list(opt.devices) or [0]
     ranges = [(first + a, first + b) for a, b in shard_ranges(n, len(devices))]
     done = [0]
