@@ -22,6 +22,14 @@ __device__ __forceinline__ int bv_reflect101(int i, int n)
     return i;
 }
 
+// KBND_SYMMETRIC of the iqa convolutions (float_ssim / float_ms_ssim): -1 -> 0 ; n -> n-1
+__device__ __forceinline__ int bv_sym(int i, int n)
+{
+    if (i < 0) return -1 - i;
+    if (i >= n) return 2 * n - i - 1;
+    return i;
+}
+
 // ---- reductions ---------------------------------------------------------------------------
 __device__ __forceinline__ long long bv_warp_sum(long long v)
 {
@@ -130,7 +138,7 @@ template <> struct Px4<int32_t> {
 };
 
 // Loads 4 consecutive pixels of row `row` starting at column gx0 (may hang over either image edge:
-// resolved per element then, BORDER 0 = libvmaf MIRROR, 1 = reflect-101).  One vector load when the
+// resolved per element then, BORDER 0 = libvmaf MIRROR, 1 = reflect-101, 2 = iqa SYMMETRIC).  One vector load when the
 // group is interior and aligned.
 template <typename T, int BORDER = 0>
 __device__ __forceinline__ typename Px4<T>::V load_px4(const uint8_t *row, int gx0, int w, int far, bool vec)
@@ -143,7 +151,7 @@ __device__ __forceinline__ typename Px4<T>::V load_px4(const uint8_t *row, int g
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int g = min(max(gx0 + k, lo), far);
-        ix[k] = BORDER == 0 ? bv_mirror(g, w) : bv_reflect101(g, w);
+        ix[k] = BORDER == 0 ? bv_mirror(g, w) : (BORDER == 1 ? bv_reflect101(g, w) : bv_sym(g, w));
     }
     return Px4<T>::pack(__ldg(p + ix[0]), __ldg(p + ix[1]), __ldg(p + ix[2]), __ldg(p + ix[3]));
 }
