@@ -9,52 +9,77 @@
 
 namespace {
 
-constexpr int MB_TW = 128;   // output tile width
-constexpr int MB_TH = 16;    // output tile height
-constexpr int MB_R = 2;      // filter radius
+// Tile = 128 x 32 outputs; the staged window starts 4 columns left of the tile so that 4-pixel vector
+// loads stay aligned.  Register-blocked: 8 outputs per item in both passes (12 inputs in registers).
+constexpr int MB_TW = 128, MB_TH = 32, MB_R = 2;
+constexpr int MB_IN_W = MB_TW + 8, MB_IN_H = MB_TH + 2 * MB_R, MB_G = MB_IN_W / 4, MB_P = MB_IN_W + 2, MB_O = 8;
+constexpr int MB_VP = MB_IN_W + 1;       // odd u32 pitch of the vertical-pass plane
 
 __constant__ unsigned c_motion_filter[5] = { 3571, 16004, 26386, 16004, 3571 };
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 motion_blur_kernel(BvBatch batch, BvPlane src, int bpc, int w, int h, uint16_t *__restrict__ blur,
-                   size_t blur_frame_elems)
+                   size_t blur_frame_elems, int vec_ok)
 {
-    __shared__ uint16_t s_in[MB_TH + 2 * MB_R][MB_TW + 2 * MB_R];
-    __shared__ uint16_t s_v[MB_TH][MB_TW + 2 * MB_R];
+    __shared__ uint16_t s_in[MB_IN_H * MB_P];
+    __shared__ unsigned s_v[MB_TH * MB_VP];
 
     const int f = blockIdx.z;
     const uint8_t *img = src.p[f];
-    const int x0 = blockIdx.x * MB_TW, y0 = blockIdx.y * MB_TH;
+    const int x0 = blockIdx.x * MB_TW - 4, y0 = blockIdx.y * MB_TH - MB_R;
     const int tid = threadIdx.x;
 
-    for (int idx = tid; idx < (MB_TH + 2 * MB_R) * (MB_TW + 2 * MB_R); idx += 256) {
-        const int r = idx / (MB_TW + 2 * MB_R), c = idx - r * (MB_TW + 2 * MB_R);
-        const int gy = bv_mirror(min(y0 + r - MB_R, h + MB_R - 1), h);
-        const int gx = bv_mirror(min(x0 + c - MB_R, w + MB_R - 1), w);
-        s_in[r][c] = (uint16_t)bv_ld<T>(img, src.pitch, gy, gx);
+    for (int g = tid; g < MB_IN_H * MB_G; g += 256) {
+        const int r = g / MB_G, gc = g - r * MB_G;
+        const int gy = bv_mirror(min(y0 + r, h + MB_R - 1), h);
+        unsigned u[4];
+        Px4<T>::raw(load_px4<T>(img + (size_t)gy * src.pitch, x0 + 4 * gc, w, w + MB_R - 1, vec_ok), u);
+        unsigned *p = reinterpret_cast<unsigned *>(s_in + r * MB_P + 4 * gc);
+        p[0] = u[0] | (u[1] << 16); p[1] = u[2] | (u[3] << 16);
     }
     __syncthreads();
 
     const unsigned add_v = 1u << (bpc - 1);
-    for (int idx = tid; idx < MB_TH * (MB_TW + 2 * MB_R); idx += 256) {
-        const int r = idx / (MB_TW + 2 * MB_R), c = idx - r * (MB_TW + 2 * MB_R);
-        unsigned acc = 0;
+    for (int item = tid; item < MB_IN_W * (MB_TH / MB_O); item += 256) {
+        const int c = item % MB_IN_W, strip = item / MB_IN_W;
+        unsigned v[MB_O + 4];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) acc += c_motion_filter[k] * (unsigned)s_in[r + k][c];
-        s_v[r][c] = (uint16_t)((acc + add_v) >> bpc);
+        for (int i = 0; i < MB_O + 4; ++i) v[i] = s_in[(MB_O * strip + i) * MB_P + c];
+#pragma unroll
+        for (int o = 0; o < MB_O; ++o) {
+            unsigned acc = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) acc += c_motion_filter[k] * v[o + k];
+            s_v[(MB_O * strip + o) * MB_VP + c] = (acc + add_v) >> bpc;
+        }
     }
     __syncthreads();
 
     uint16_t *out = blur + (size_t)f * blur_frame_elems;
-    for (int idx = tid; idx < MB_TH * MB_TW; idx += 256) {
-        const int r = idx / MB_TW, c = idx - r * MB_TW;
-        const int gy = y0 + r, gx = x0 + c;
-        if (gy < h && gx < w) {
+    for (int item = tid; item < MB_TH * (MB_TW / MB_O); item += 256) {
+        const int r = item % MB_TH, g = item / MB_TH;
+        unsigned v[MB_O + 4];
+#pragma unroll
+        for (int i = 0; i < MB_O + 4; ++i) v[i] = s_v[r * MB_VP + MB_O * g + 2 + i];     // output col j <-> staged col j + 4
+        const int gy = y0 + MB_R + r, gx0 = x0 + 4 + MB_O * g;
+        if (gy >= h) continue;
+        unsigned res[MB_O];
+#pragma unroll
+        for (int o = 0; o < MB_O; ++o) {
             unsigned acc = 0;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) acc += c_motion_filter[k] * (unsigned)s_v[r][c + k];
-            out[(size_t)gy * w + gx] = (uint16_t)((acc + 32768u) >> 16);
+            for (int k = 0; k < 5; ++k) acc += c_motion_filter[k] * v[o + k];
+            res[o] = (acc + 32768u) >> 16;
+        }
+        uint16_t *dst = out + (size_t)gy * w + gx0;
+        if ((w & 7) == 0 && (blur_frame_elems & 7) == 0 && gx0 + MB_O <= w) {
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(res[0] | (res[1] << 16), res[2] | (res[3] << 16),
+                                                         res[4] | (res[5] << 16), res[6] | (res[7] << 16));
+        } else {
+#pragma unroll
+            for (int o = 0; o < MB_O; ++o)
+                if (gx0 + o < w) dst[o] = (uint16_t)res[o];
         }
     }
 }
@@ -99,10 +124,13 @@ void bv_launch_motion_blur(const BvBatch &b, BvPlane ref_y, int bpc, int w, int 
 {
     dim3 grid((w + MB_TW - 1) / MB_TW, (h + MB_TH - 1) / MB_TH, b.n);
     bv_prof_begin(L, BVK_MOTION_BLUR);
+    size_t bits = ref_y.pitch;
+    for (int k = 0; k < b.n; ++k) bits |= (size_t)ref_y.p[k];
+    const int vec_ok = (bits & (bpc == 8 ? 3 : 7)) == 0;
     if (bpc == 8)
-        motion_blur_kernel<uint8_t><<<grid, 256, 0, L.st>>>(b, ref_y, bpc, w, h, blur_cur, blur_frame_elems);
+        motion_blur_kernel<uint8_t><<<grid, 256, 0, L.st>>>(b, ref_y, bpc, w, h, blur_cur, blur_frame_elems, vec_ok);
     else
-        motion_blur_kernel<uint16_t><<<grid, 256, 0, L.st>>>(b, ref_y, bpc, w, h, blur_cur, blur_frame_elems);
+        motion_blur_kernel<uint16_t><<<grid, 256, 0, L.st>>>(b, ref_y, bpc, w, h, blur_cur, blur_frame_elems, vec_ok);
     bv_prof_end(L, BVK_MOTION_BLUR);
 }
 
