@@ -88,6 +88,7 @@ struct bv_ctx {
     // vif
     BvVifLevels vif_lv;
     uint16_t *d_log2 = nullptr;
+    uint8_t *d_log2c = nullptr;         // compressed log2 table (see alloc_ctx)
     // adm
     BvAdmBuffers adm;
     BvAdmScaleParams adm_sp[4];
@@ -150,6 +151,18 @@ int alloc_ctx(bv_ctx *c)
         for (unsigned i = 32767; i < 65536; ++i) tab[i] = (uint16_t)round(log2f((float)i) * 2048);
         CK(cudaMalloc(&c->d_log2, sizeof(uint16_t) * 65536));
         CK(cudaMemcpy(c->d_log2, tab.data(), sizeof(uint16_t) * 65536, cudaMemcpyHostToDevice));
+        // Compressed copy for shared memory (the table is monotone with slope < 0.1 per entry): 512 u16 bases,
+        // one per 64 entries, followed by 32768 4-bit deltas -> 17 KB instead of 64 KB.  Exact by construction.
+        std::vector<uint8_t> packed(BV_LOG2C_BYTES, 0);
+        uint16_t *base = reinterpret_cast<uint16_t *>(packed.data());
+        for (unsigned j = 0; j < 32768; ++j) {
+            const unsigned i = 32768 + j, b = tab[i & ~63u], d = tab[i] - b;
+            if (d > 15u) return fail(c, BV_ERR_UNSUPPORTED, "log2 table does not compress to 4-bit deltas");
+            base[j >> 6] = (uint16_t)b;
+            packed[1024 + (j >> 1)] |= (uint8_t)(d << ((j & 1) * 4));
+        }
+        CK(cudaMalloc(&c->d_log2c, BV_LOG2C_BYTES));
+        CK(cudaMemcpy(c->d_log2c, packed.data(), BV_LOG2C_BYTES, cudaMemcpyHostToDevice));
         int lw = c->w, lh = c->h;
         c->vif_lv.w[0] = lw; c->vif_lv.h[0] = lh;
         c->vif_lv.ref[0] = c->vif_lv.dis[0] = nullptr; c->vif_lv.frame_elems[0] = 0;
@@ -351,7 +364,7 @@ int launch_group(bv_ctx *c, Group &g)
         c->blur_cur ^= 1;
     }
     if (c->feat & BV_FEAT_VIF)
-        bv_launch_vif(b, ry, dy, c->bpc, c->vif_lv, c->d_log2, c->opts.vif_enhn_gain_limit, g.d_raw, L);
+        bv_launch_vif(b, ry, dy, c->bpc, c->vif_lv, c->d_log2, c->d_log2c, c->opts.vif_enhn_gain_limit, g.d_raw, L);
     if (c->feat & BV_FEAT_ADM) {
         CK(cudaMemsetAsync(c->adm.rows, 0, sizeof(unsigned long long) * c->adm.rows_frame_stride * g.n, st));
         bv_launch_adm(b, ry, dy, c->bpc, c->adm, c->adm_sp, c->opts.adm_enhn_gain_limit, g.d_raw, L);
@@ -513,6 +526,7 @@ void bv_destroy(bv_ctx *c)
     }
     for (int k = 0; k < 2; ++k) if (c->blur[k]) cudaFree(c->blur[k]);
     if (c->d_log2) cudaFree(c->d_log2);
+    if (c->d_log2c) cudaFree(c->d_log2c);
     if (c->feat & BV_FEAT_VIF) for (int s = 1; s < 4; ++s) { if (c->vif_lv.ref[s]) cudaFree(c->vif_lv.ref[s]); if (c->vif_lv.dis[s]) cudaFree(c->vif_lv.dis[s]); }
     if (c->feat & BV_FEAT_ADM) { for (int s = 0; s < 3; ++s) if (c->adm.bands[s]) cudaFree(c->adm.bands[s]); if (c->adm.rows) cudaFree(c->adm.rows); }
     if (c->d_div) cudaFree(c->d_div);

@@ -233,8 +233,10 @@ struct BvVifLevels {                        // u16 pyramid levels 1..3 (tight pi
     size_t frame_elems[4];
     int w[4], h[4];
 };
+#define BV_LOG2C_BYTES (1024 + 16384)       // 512 u16 bases + 32768 4-bit deltas
 void bv_launch_vif(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, const BvVifLevels &lv,
-                   const uint16_t *log2_table, double egl, unsigned long long *raw, const BvLaunch &L);
+                   const uint16_t *log2_table, const uint8_t *log2_packed, double egl, unsigned long long *raw,
+                   const BvLaunch &L);
 // adm
 struct BvAdmBuffers {
     void *bands[4];                         // scale s: [frame][ref/dis][a,v,h,d][h][w], i16 (s=0) / i32
