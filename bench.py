@@ -139,6 +139,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel: str, wname: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture of this workload (profiles/r01_traffic.json: {workload: {kernel: {"bytes": .., "frames": ..}}})."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        e = t[wname][kernel]
+        return e
+    except Exception:
+        return None
+
+
 def measured_peaks() -> tuple:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -173,12 +184,17 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_baseline(wl: dict, frames_per_core: int = 2) -> dict:
+def cpu_baseline(wl: dict, frames_per_core: int = 0) -> dict:
     import multiprocessing as mp
     import oracle
     oracle.build()
     cores = os.cpu_count() or 1
     kind = "float" if "float" in wl["model"] else "int"
+    if frames_per_core <= 0:
+        # ~10-20 s of CPU work per core: the scalar C oracle needs ~1 s (float + ssim + ms-ssim) or ~0.5 s
+        # (integer) per 1080p frame pair, 4x that at 4K
+        per_frame = (1.1 if kind == "float" else 0.5) * (wl["w"] * wl["h"]) / (1920 * 1080)
+        frames_per_core = max(2, min(24, int(round(12.0 / per_frame))))
     jobs = [(1, 10 * c, frames_per_core, wl["w"], wl["h"], wl["bpc"], kind) for c in range(cores)]
     t0 = time.perf_counter()
     with mp.get_context("spawn").Pool(cores) as pool:
@@ -200,7 +216,7 @@ def reference_arm(args, wl, wname):
     times = []
     base = None
     for s in range(args.warmup + args.steps):
-        base = cpu_baseline(wl, frames_per_core=1)
+        base = cpu_baseline(wl, frames_per_core=max(1, min(4, int(round(3.0 / ((1.1 if 'float' in wl['model'] else 0.5) * wl['w'] * wl['h'] / (1920 * 1080)))))))
         if s >= args.warmup:
             times.append(base["value"])
     v = statistics.mean(times) if times else 0.0
@@ -377,8 +393,12 @@ def main() -> int:
     if top:
         by = kernel_bytes(top, w, h, bps)
         ach = kernels[top]["gbps"]
+        tr = ncu_traffic(top, wname)
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (ach / peak) if ach else None,
+                    "traffic": (tr["bytes"] * B / tr["frames"]) if tr else None,
+                    "traffic_source": (tr.get("source") if tr else None), "peak_source": peak_src,
+                    "pipe_note": (tr.get("pipe_note") if tr else None),
                     "algorithmic_bytes_per_launch": by * B if by else None,
                     "ms_per_launch": kernels[top]["ms_per_launch"], "frames_per_launch": B,
                     "share_of_step": kernels[top]["ms_per_launch"] / tot_ms,
