@@ -10,8 +10,8 @@ stats-file layout; reference
 
 Differences, all forced by the environment:
 * PyQt5 is optional.  Without it the four signals are plain objects with ``connect`` / ``emit``.
-* Inputs are raw planar video (``.y4m`` or headerless ``.yuv`` with a ``_WxH`` name hint); container
-  decode (the reference's aligned MP4s) belongs to the "next" rows of the scope table.
+* Inputs are raw planar video (``.y4m`` or headerless ``.yuv`` with a ``_WxH`` name hint) or, when cv2 is
+  installed, containers (``.mp4`` ...) decoded by its bundled libavcodec -- luma only, which is all VMAF reads.
 * ``threads`` (libvmaf ``n_threads``) is accepted and ignored: the work runs on the GPUs in
   ``devices`` (default: every visible B200), frame-sharded with a one-frame lead-in per shard.
 """

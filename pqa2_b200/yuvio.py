@@ -25,6 +25,7 @@ class ClipInfo:
     nb_frames: int = 0
     header_bytes: int = 0
     frame_header_bytes: int = 0
+    decoder: str = "raw"          # "raw" (y4m / planar yuv) or "cv2" (container decoded by cv2's bundled libavcodec, luma only)
 
     @property
     def fps(self) -> float:
@@ -96,6 +97,8 @@ def probe(path: str, width: int | None = None, height: int | None = None, pix_fm
             info.nb_frames = (size - info.header_bytes) // per
             return info
     name = os.path.basename(path)
+    if os.path.splitext(name)[1].lower() in _CONTAINER_EXT:
+        return _probe_container(path)
     if width is None or height is None:
         m = re.search(r"(\d{2,5})x(\d{2,5})", name)
         if not m:
@@ -115,8 +118,76 @@ def probe(path: str, width: int | None = None, height: int | None = None, pix_fm
     return info
 
 
+_CONTAINER_EXT = {".mp4", ".mov", ".mkv", ".avi", ".m4v", ".webm", ".ts"}
+
+
+def _probe_container(path: str) -> ClipInfo:
+    """Compressed clips (the reference's aligned H.264 MP4s, app/bookend_alignment.py:526-536) through the
+    libavcodec that ships inside cv2.  With CAP_PROP_CONVERT_RGB off cv2 hands back the decoder's luma plane
+    untouched, which is all the VMAF extractors, psnr_y, float_ssim and float_ms_ssim read; chroma is not
+    exposed, so such clips are described as 8-bit luma-only (chroma-plane stats files are skipped for them)."""
+    try:
+        import cv2
+    except Exception as e:                                  # noqa: BLE001
+        raise ValueError(f"{path}: container input needs cv2 (not installed): {e}")
+    cap = cv2.VideoCapture(path)
+    try:
+        if not cap.isOpened():
+            raise ValueError(f"{path}: cv2 cannot open this file")
+        w, h = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+        n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        fps = float(cap.get(cv2.CAP_PROP_FPS)) or 30.0
+    finally:
+        cap.release()
+    if w <= 0 or h <= 0:
+        raise ValueError(f"{path}: no video stream")
+    return ClipInfo(path, w, h, 8, 400, int(round(fps * 1000)), 1000, nb_frames=n, decoder="cv2")
+
+
+class _Cv2Reader:
+    """Luma planes of a container file, decoded by cv2 (sequential; seeks when asked for another frame)."""
+
+    def __init__(self, info: ClipInfo):
+        import cv2
+        self.info, self._cv2 = info, cv2
+        try:                                               # cv2 warns on every frame that yuv420p is handed back raw
+            cv2.utils.logging.setLogLevel(cv2.utils.logging.LOG_LEVEL_ERROR)
+        except Exception:                                  # noqa: BLE001
+            pass
+        self._cap = cv2.VideoCapture(info.path)
+        self._cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+        self._next = 0
+
+    def close(self):
+        self._cap.release()
+
+    def alloc_planes(self, pinned: bool = True):
+        if pinned:
+            from .extractor import pinned_empty
+            return [pinned_empty((self.info.height, self.info.width), np.uint8)]
+        return [np.empty((self.info.height, self.info.width), np.uint8)]
+
+    def read_into(self, i: int, planes, luma_only: bool = False) -> None:
+        if i != self._next:
+            self._cap.set(self._cv2.CAP_PROP_POS_FRAMES, i)
+        ok, fr = self._cap.read()
+        if not ok or fr is None:
+            raise EOFError(f"{self.info.path}: cannot decode frame {i}")
+        self._next = i + 1
+        h, w = self.info.height, self.info.width
+        if fr.ndim == 3:                                    # backend ignored CONVERT_RGB=0: BGR -> BT.601 luma
+            fr = self._cv2.cvtColor(fr, self._cv2.COLOR_BGR2YUV)[:, :, 0]
+        y = fr.reshape(-1, w)[:h]                           # (h, w) luma; some builds return the whole I420 buffer (3h/2, w)
+        planes[0][...] = y
+
+
 class ClipReader:
     """Sequential / random access reader that fills caller-provided (pinned) plane arrays."""
+
+    def __new__(cls, info: ClipInfo):
+        if getattr(info, "decoder", "raw") == "cv2":
+            return _Cv2Reader(info)
+        return super().__new__(cls)
 
     def __init__(self, info: ClipInfo):
         self.info = info

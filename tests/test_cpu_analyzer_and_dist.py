@@ -156,3 +156,31 @@ def test_two_rank_gloo_matches_single_process(n):
     for a, b in zip(metrics, frames):
         assert a == b["metrics"]                     # bit-identical, incl. motion2 across the shard boundary
     assert D.rank_range(7, 0, 2) == (0, 3) and D.rank_range(7, 1, 2) == (3, 7) and D.rank_range(1, 1, 2) == (1, 1)
+
+
+def test_container_decode_through_cv2(tmp_path):
+    """Row f2 (decode): compressed clips come in through cv2's bundled libavcodec, luma plane untouched."""
+    cv2 = pytest.importorskip("cv2")
+    from pqa2_b200 import synth
+    w, h, n = 320, 176, 6
+    path = str(tmp_path / "clip.mp4")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 25, (w, h))
+    if not wr.isOpened():
+        pytest.skip("cv2 cannot encode mp4v here")
+    lum = [synth.ref_luma(1, f, w, h) for f in range(n)]
+    for y in lum:
+        wr.write(cv2.cvtColor(y, cv2.COLOR_GRAY2BGR))
+    wr.release()
+    info = yuvio.probe(path)
+    assert (info.width, info.height, info.bpc, info.chroma, info.nb_frames, info.decoder) == (w, h, 8, 400, n, "cv2")
+    assert abs(info.fps - 25.0) < 1e-6
+    r = yuvio.ClipReader(info)
+    pl = r.alloc_planes(pinned=False)
+    for f in (0, 1, 4, 2):                       # sequential and seeking reads
+        r.read_into(f, pl, True)
+        # limited-range luma of a lossy encode: 16 + 219/255 * gray, within a few code values on average
+        want = 16.0 + lum[f].astype(np.float64) * (219.0 / 255.0)
+        assert pl[0].shape == (h, w) and np.abs(pl[0] - want).mean() < 4.0
+    r.close()
+    meta = VMAFAnalyzer().get_video_metadata(path)
+    assert meta["width"] == w and meta["nb_frames"] == n

@@ -276,3 +276,32 @@ def test_shard_invariance_and_batch_of_clips():
         assert "error" not in batch[k]
         assert [fr["metrics"] for fr in batch[k]["frames"]] == [fr["metrics"] for fr in solo["frames"]]
         assert batch[k]["pooled_metrics"]["vmaf"] == solo["pooled_metrics"]["vmaf"]
+
+
+def test_analyzer_on_mp4_inputs(tmp_path):
+    """The reference's real inputs are H.264/MPEG-4 MP4s (app/bookend_alignment.py:526-536): decode through cv2,
+    score the luma on the GPU, same files and dict as for raw clips."""
+    cv2 = pytest.importorskip("cv2")
+    from pqa2_b200.vmaf_analyzer import VMAFAnalyzer
+    w, h, n = 320, 176, 8
+    paths = []
+    for name, q in (("ref", None), ("dis", 6)):
+        p = str(tmp_path / f"{name}.mp4")
+        wr = cv2.VideoWriter(p, cv2.VideoWriter_fourcc(*"mp4v"), 25, (w, h))
+        if not wr.isOpened():
+            pytest.skip("cv2 cannot encode mp4v here")
+        for f in range(n):
+            y = synth.ref_luma(2, f, w, h)
+            if q:
+                y = synth.distort(y, 2, f, 8, q)
+            wr.write(cv2.cvtColor(y, cv2.COLOR_GRAY2BGR))
+        wr.release()
+        paths.append(p)
+    a = VMAFAnalyzer()
+    a.set_output_directory(str(tmp_path))
+    errs = []
+    a.error_occurred.connect(errs.append)
+    res = a.analyze_videos(paths[0], paths[1])
+    assert not errs and res is not None and 0 < res["vmaf_score"] < 100 and len(res["raw_results"]["frames"]) == n
+    same = a.analyze_videos(paths[0], paths[0])
+    assert same["vmaf_score"] >= 97.4                        # identical pair: adm2 = vif = 1 -> 97.43 at motion 0, more with motion
