@@ -225,7 +225,7 @@ def reference_arm(args, wl, wname):
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1000.0 * (os.cpu_count() or 1) / v if v else None, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": wl_dtype(wl), "data": "synthetic",
-           "config": bench_config(wl, wname, 0, args.gpus),
+           "config": bench_config(wl, wname, args.frames_per_step or wl["frames_per_step"], args.gpus),
            "cpu_baseline": base, "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0,
            "note": "CPU restatement of the libvmaf path (oracle/), all host cores; ffmpeg+libvmaf is not installable here"}

@@ -184,3 +184,23 @@ def test_container_decode_through_cv2(tmp_path):
     r.close()
     meta = VMAFAnalyzer().get_video_metadata(path)
     assert meta["width"] == w and meta["nb_frames"] == n
+
+
+def test_libvmaf_filter_string_round_trip():
+    """Rows a4 / a15: the reference's option builder (app/vmaf_analyzer.py:373-406) and the legacy call site's
+    string (app/ui/tabs/results_tab.py:346-350) both map onto engine options."""
+    from pqa2_b200 import options as O
+    s = O.build_libvmaf_filter("/out/T_1_vmaf.json", "vmaf_v0.6.1", threads=8, feature_subsample=3)
+    assert s == "libvmaf=log_path=/out/T_1_vmaf.json:log_fmt=json:model=version=vmaf_v0.6.1:n_threads=8:n_subsample=3"
+    p = O.parse_libvmaf_filter(s)
+    assert (p["model"], p["log_path"], p["log_fmt"], p["n_threads"], p["pool"]) == ("vmaf_v0.6.1", "/out/T_1_vmaf.json", "json", 8, "mean")
+    assert p["options"].n_subsample == 3 and not p["options"].psnr and not p["options"].ssim
+    s = O.build_libvmaf_filter("C:/r/x_vmaf.json", "C:/models/custom.json", pool_method="harmonic_mean",
+                               enable_motion_score=True, enable_temporal_features=True)
+    assert ":pool=harmonic_mean:psnr=1:ssim=1:" in s and s.count("feature=name=motion:enable=1") == 3
+    p = O.parse_libvmaf_filter(s)
+    assert p["model"] == "C:/models/custom.json" and p["log_path"] == "C:/r/x_vmaf.json" and p["pool"] == "harmonic_mean"
+    assert p["options"].psnr and p["options"].ssim and "vif_scale0" in p["features"] and "adm2" in p["features"]
+    legacy = O.parse_libvmaf_filter("libvmaf=log_fmt=json:log_path=/tmp/vmaf.json:psnr=1:ssim=1:model_path=/m/vmaf_v0.6.1.json")
+    assert legacy["model"] == "/m/vmaf_v0.6.1.json" and legacy["options"].psnr and legacy["options"].ssim
+    assert M.resolve_model(O.parse_libvmaf_filter("libvmaf=model=version=vmaf_4k_v0.6.1")["model"]).name == "vmaf_4k_v0.6.1"
