@@ -305,3 +305,52 @@ def test_analyzer_on_mp4_inputs(tmp_path):
     assert not errs and res is not None and 0 < res["vmaf_score"] < 100 and len(res["raw_results"]["frames"]) == n
     same = a.analyze_videos(paths[0], paths[0])
     assert same["vmaf_score"] >= 97.4                        # identical pair: adm2 = vif = 1 -> 97.43 at motion 0, more with motion
+
+
+def test_strided_host_planes_and_12bit():
+    """Planes that are views into larger arrays (row stride != width) go through the 2-D copy path; 12-bit
+    samples use the same u16 kernels with their own shifts."""
+    w, h = 200, 120
+    frames = [synth.frame_pair(23, f, w, h, 8, chroma=False) for f in range(2)]
+    rows = _oracle_rows(frames, w, h, 8)
+    big_r = [np.zeros((h, w + 56), np.uint8) for _ in frames]
+    big_d = [np.zeros((h, w + 24), np.uint8) for _ in frames]
+    with FeatureExtractor(w, h, 8, 0, L.FEAT_VMAF_INT | L.FEAT_PSNR_Y) as fx:
+        for f, (rp, dp) in enumerate(frames):
+            big_r[f][:, 8:8 + w] = rp[0]
+            big_d[f][:, :w] = dp[0]
+            fx.submit(f, [big_r[f][:, 8:8 + w]], [big_d[f][:, :w]], L.FRAME_FIRST if f == 0 else 0)
+        out = fx.fetch()
+    for f in range(2):
+        _check(out[f], rows[f], w, h, 8, planes=1)
+    frames = [synth.frame_pair(29, f, 208, 120, 12, chroma=False) for f in range(2)]
+    rows = _oracle_rows(frames, 208, 120, 12)
+    with FeatureExtractor(208, 120, 12, 0, L.FEAT_VMAF_INT | L.FEAT_PSNR_Y) as fx:
+        for f, (rp, dp) in enumerate(frames):
+            fx.submit(f, rp, dp, L.FRAME_FIRST if f == 0 else 0)
+        out = fx.fetch()
+    for f in range(2):
+        _check(out[f], rows[f], 208, 120, 12, planes=1)
+
+
+def test_engine_subsample_and_cancel():
+    """n_subsample (reference :379): VIF/ADM on every N-th frame, motion on all; terminate -> None."""
+    import threading
+    from pqa2_b200 import engine, model as M
+    w, h, n = 320, 180, 9
+    model = M.resolve_model("vmaf_v0.6.1")
+    src = engine.SynthSource(w, h, 8, n, seed=19, chroma=0)
+    full = engine.analyze(src, model, engine.EngineOptions())
+    sub = engine.analyze(src, model, engine.EngineOptions(n_subsample=3))
+    assert [fr["frameNum"] for fr in sub["frames"]] == [0, 3, 6]
+    byn = {fr["frameNum"]: fr["metrics"] for fr in full["frames"]}
+    for fr in sub["frames"]:
+        assert fr["metrics"] == byn[fr["frameNum"]]          # same per-frame values, motion2 from all frames
+    ev = threading.Event()
+    ev.set()
+    assert engine.analyze(src, model, engine.EngineOptions(), cancel=ev) is None
+    # the context stays usable after a cancel inside a session
+    with engine.Engine() as sess:
+        assert sess.analyze(src, model, engine.EngineOptions(), cancel=ev) is None
+        again = sess.analyze(src, model, engine.EngineOptions())
+        assert [fr["metrics"] for fr in again["frames"]] == [fr["metrics"] for fr in full["frames"]]
