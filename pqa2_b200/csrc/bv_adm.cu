@@ -10,7 +10,8 @@
 // adm_rows_finish applies the row shift and adds the rows.  All arithmetic is integer except the
 // angle test and the gain limit, which follow the C promotion rules in IEEE double (no FMA).
 //
-// CTA = 64x16 band pixels (+1 halo for the 3x3 threshold) = 134x38 input samples per picture.
+// Persistent CTAs (2 per SM) loop over (frame, tile) items; tile = 64x16 band pixels (+1 halo for the 3x3
+// threshold) = 136x38 staged input samples per picture, prefetched into registers one tile ahead.
 #include "bv_common.cuh"
 #include "../../include/b200vmaf.h"
 #include <math.h>
