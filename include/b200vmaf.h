@@ -119,6 +119,8 @@ int  bv_submit_device(bv_ctx *, int64_t frame_index, const void *const ref_plane
                       const void *const dis_planes[3], const size_t dis_stride[3], unsigned frame_flags);
 int  bv_wait_uploads(bv_ctx *);          /* all submitted host buffers may be reused after this */
 int  bv_flush(bv_ctx *);                 /* launch the partial group and drain every stream     */
+int  bv_kick(bv_ctx *);                  /* launch the partial group now, without draining: lets a caller start the
+                                            GPU on the first few frames of a clip instead of waiting for a full group */
 int64_t bv_frames_done(bv_ctx *);        /* frames whose features are ready (non-blocking)      */
 /* Copy out features of `count` frames starting at submission ordinal `first` (0-based, in
  * submission order incl. lead-in frames); blocks until they are ready. */

@@ -605,6 +605,16 @@ int bv_flush(bv_ctx *c)
     return 0;
 }
 
+int bv_kick(bv_ctx *c)
+{
+    if (!c) return BV_ERR_ARG;
+    if (c->cancelled.load()) return fail(c, BV_ERR_CANCELLED, "cancelled");
+    CK(cudaSetDevice(c->device));
+    Group &g = c->groups[c->cur];
+    if (!g.in_flight && g.n > 0) return launch_group(c, g);
+    return 0;
+}
+
 int64_t bv_frames_done(bv_ctx *c) { return c ? c->ready.load() : 0; }
 
 int bv_reset(bv_ctx *c)

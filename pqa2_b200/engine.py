@@ -130,6 +130,9 @@ def shard_ranges(n_frames: int, n_shards: int):
     return [(g * n_frames // n_shards, (g + 1) * n_frames // n_shards) for g in range(n_shards)]
 
 
+_FIRST_KICK = 8
+
+
 class _Cancelled(Exception):
     pass
 
@@ -184,6 +187,8 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
                 flags |= L.FRAME_SKIP_SPATIAL
             fx.submit(i, rp, dp, flags)
             ordinal += 1
+            if ordinal == _FIRST_KICK and B > _FIRST_KICK:
+                fx.kick()                   # start the GPU on a short first group: the pipeline fills 4x sooner
             if progress:
                 progress(1)
         fx.flush()

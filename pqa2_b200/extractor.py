@@ -112,6 +112,10 @@ class FeatureExtractor:
         self._check(self.lib.bv_flush(self._ctx))
         self._keep.clear()
 
+    def kick(self):
+        """Launch the frames submitted so far (a partial group) without waiting for them."""
+        self._check(self.lib.bv_kick(self._ctx))
+
     def cancel(self):
         self.lib.bv_cancel(self._ctx)
 
