@@ -1,7 +1,7 @@
 """Command line: score a reference/distorted pair of raw clips the way the reference's ffmpeg call does.
 
     python -m pqa2_b200 REF.y4m DIST.y4m [--model vmaf_v0.6.1] [--out DIR] [--name TEST] [--pool mean]
-                        [--subsample N] [--no-psnr] [--no-ssim] [--gpus 0,1,...]
+                        [--subsample N] [--no-psnr] [--no-ssim] [--gpus 0,1,...] [--align-bookends]
 
 Equivalent of `ffmpeg -i DIST -i REF -lavfi libvmaf=log_path=...:log_fmt=json:model=version=<m>:n_subsample=<N>`
 plus the two `psnr` / `ssim` passes (reference app/vmaf_analyzer.py:373-419, :996-1092)."""
@@ -25,6 +25,9 @@ def main(argv=None) -> int:
     ap.add_argument("--no-psnr", action="store_true")
     ap.add_argument("--no-ssim", action="store_true")
     ap.add_argument("--gpus", default=None, help="comma-separated GPU ordinals (default: all)")
+    ap.add_argument("--align-bookends", action="store_true",
+                    help="DIST is a capture with white bookends: find the content window on the GPU and trim/re-time it "
+                         "losslessly before scoring (reference app/bookend_alignment.py)")
     a = ap.parse_args(argv)
 
     an = VMAFAnalyzer()
@@ -37,7 +40,17 @@ def main(argv=None) -> int:
         an.set_devices([int(x) for x in a.gpus.split(",")])
     an.error_occurred.connect(lambda m: print("error:", m, file=sys.stderr))
     an.status_update.connect(lambda m: print(m, file=sys.stderr))
-    res = an.analyze_videos(a.reference, a.distorted, a.model)
+    ref, dis = a.reference, a.distorted
+    if a.align_bookends:
+        from . import alignment
+        al = alignment.align_bookend_videos(ref, dis, a.out)
+        if al is None:
+            print("error: Failed to detect white bookends in captured video", file=sys.stderr)
+            return 1
+        ref, dis = al["aligned_reference"], al["aligned_captured"]
+        print("aligned: %d frames, captured frames %d..%d" % (al["plan"].n_frames, al["plan"].cap_frames[0],
+                                                               al["plan"].cap_frames[-1]), file=sys.stderr)
+    res = an.analyze_videos(ref, dis, a.model)
     if res is None:
         return 1
     print("VMAF score: %.6f" % res["vmaf_score"])

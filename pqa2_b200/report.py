@@ -126,3 +126,86 @@ def write_frames_csv(path: str, frames: list) -> None:
         wr.writerow(["Frame Number"] + keys)
         for fr in frames:
             wr.writerow([fr["frameNum"]] + ["%.4f" % fr["metrics"].get(k, 0.0) for k in keys])
+
+
+def _mean_of(pooled: dict, *names):
+    for n in names:
+        if n in pooled and "mean" in pooled[n]:
+            return pooled[n]["mean"]
+    return None
+
+
+def _fmt4(v) -> str:
+    if v is None:
+        return "N/A"
+    return v if isinstance(v, str) else "%.4f" % v
+
+
+def write_result_csv(path: str, test_name: str, data: dict, reference_path: str = "Unknown",
+                     distorted_path: str = "Unknown", date: str | None = None) -> str:
+    """One test as the Results tab exports it (``ResultsTab.export_result_csv``,
+    ``app/ui/tabs/results_tab.py:3518-3616``): summary row, file rows, then the per-frame table."""
+    import datetime as _dt
+    pooled = data.get("pooled_metrics", {})
+    with open(path, "w", newline="") as f:
+        wr = csv.writer(f)
+        wr.writerow(["Test Name", "Date", "VMAF Score", "PSNR Score", "SSIM Score"])
+        wr.writerow([test_name, date or _dt.datetime.now().strftime("%Y-%m-%d %H:%M:%S"),
+                     _fmt4(_mean_of(pooled, "vmaf")), _fmt4(_mean_of(pooled, "psnr", "psnr_y")),
+                     _fmt4(_mean_of(pooled, "ssim", "ssim_y"))])
+        wr.writerow([])
+        wr.writerow(["Reference File", reference_path])
+        wr.writerow(["Distorted File", distorted_path])
+        frames = data.get("frames") or []
+        if frames:
+            wr.writerow([])
+            keys = sorted(frames[0].get("metrics", {}).keys())
+            wr.writerow(["Frame Number"] + keys)
+            for fr in frames:
+                m = fr.get("metrics", {})
+                wr.writerow([fr.get("frameNum", "N/A")] +
+                            [("%.4f" % m[k]) if isinstance(m.get(k), (int, float)) else "N/A" for k in keys])
+    return path
+
+
+def write_combined_csv(path: str, rows: list) -> str:
+    """Many tests in one table (``ResultsTab.export_combined_csv``, ``results_tab.py:3644-3696``).  ``rows``: dicts
+    with test_name, timestamp, vmaf_score, psnr_score, ssim_score, reference, duration, test_dir."""
+    with open(path, "w", newline="") as f:
+        wr = csv.writer(f)
+        wr.writerow(["Test Name", "Date/Time", "VMAF Score", "PSNR Score", "SSIM Score", "Reference", "Duration",
+                     "Test Directory"])
+        for r in rows:
+            wr.writerow([r.get("test_name", ""), r.get("timestamp", ""), _fmt4(r.get("vmaf_score")),
+                         _fmt4(r.get("psnr_score")), _fmt4(r.get("ssim_score")), r.get("reference", ""),
+                         r.get("duration", ""), r.get("test_dir", "")])
+    return path
+
+
+def write_metadata_json(path: str, results: dict, video: dict, settings: dict, test_name: str = "test",
+                        capture: dict | None = None) -> str:
+    """``<test>_<stamp>_metadata.json`` next to the log (``AnalysisTab`` writes it, ``analysis_tab.py:765-811``); the
+    History tab indexes tests by these files.  ``results``: the analyzer's result dict; ``video``: width / height /
+    fps / frame_count / duration_seconds."""
+    import json
+    import platform
+    w, h = video.get("width"), video.get("height")
+    meta = {
+        "test_name": test_name,
+        "vmaf_score": results.get("vmaf_score"),
+        "reference_video": results.get("reference_video"),
+        "distorted_video": results.get("distorted_video"),
+        "psnr_file": results.get("psnr_score") if results.get("psnr_log") else None,
+        "ssim_file": results.get("ssim_score") if results.get("ssim_log") else None,
+        "json_result": results.get("json_path") and results["json_path"].replace("\\", "/").split("/")[-1],
+        "video_details": {"resolution": f"{w}x{h}" if w and h else "Unknown", "width": w, "height": h,
+                          "fps": video.get("fps"), "frame_count": video.get("frame_count"),
+                          "duration_seconds": video.get("duration_seconds")},
+        "analysis_settings": settings,
+        "capture_details": capture or {},
+        "system_info": {"engine_version": VERSION, "os": platform.system(), "os_version": platform.version(),
+                        "processor": platform.processor()},
+    }
+    with open(path, "w") as f:
+        json.dump(meta, f, indent=4)
+    return path

@@ -121,3 +121,35 @@ def test_pooling_and_json_writer(tmp_path):
     report.write_frames_csv(str(csvp), frames)
     lines = csvp.read_text().splitlines()
     assert lines[0] == "Frame Number,integer_motion2,vmaf" and lines[2] == "1,0.5000,80.0000"
+
+
+def test_result_csv_combined_csv_and_metadata(tmp_path):
+    """Row f3: the per-test CSV, the combined CSV and the metadata file the reference's Results / History tabs
+    produce and index (app/ui/tabs/results_tab.py:3518-3696, app/ui/tabs/analysis_tab.py:765-811)."""
+    import csv
+    import json
+    from pqa2_b200 import report
+    frames = [{"frameNum": i, "metrics": {"vmaf": 90.0 + i, "psnr_y": 40.125, "integer_motion2": 0.5}} for i in range(3)]
+    data = {"frames": frames, "pooled_metrics": report.pooled_metrics(frames)}
+    p = report.write_result_csv(str(tmp_path / "t.csv"), "T1", data, "/r/ref.y4m", "/r/dis.y4m", date="2025-01-01 00:00:00")
+    rows = list(csv.reader(open(p)))
+    assert rows[0] == ["Test Name", "Date", "VMAF Score", "PSNR Score", "SSIM Score"]
+    assert rows[1] == ["T1", "2025-01-01 00:00:00", "91.0000", "40.1250", "N/A"]
+    assert rows[2] == [] and rows[3] == ["Reference File", "/r/ref.y4m"] and rows[4] == ["Distorted File", "/r/dis.y4m"]
+    assert rows[6] == ["Frame Number", "integer_motion2", "psnr_y", "vmaf"]
+    assert rows[7] == ["0", "0.5000", "40.1250", "90.0000"] and len(rows) == 10
+    p = report.write_combined_csv(str(tmp_path / "c.csv"), [
+        {"test_name": "A", "timestamp": "2025-01-01 00:00:00", "vmaf_score": 91.0, "psnr_score": "a_psnr.txt",
+         "ssim_score": None, "reference": "ref.y4m", "duration": "1.0s", "test_dir": "/x/A"}])
+    rows = list(csv.reader(open(p)))
+    assert rows[0][:5] == ["Test Name", "Date/Time", "VMAF Score", "PSNR Score", "SSIM Score"]
+    assert rows[1] == ["A", "2025-01-01 00:00:00", "91.0000", "a_psnr.txt", "N/A", "ref.y4m", "1.0s", "/x/A"]
+    res = {"vmaf_score": 91.0, "reference_video": "ref.y4m", "distorted_video": "dis.y4m", "psnr_score": "T_psnr.txt",
+           "psnr_log": "/x/T_psnr.txt", "ssim_score": "Not Available", "ssim_log": None, "json_path": "/x/T_vmaf.json"}
+    p = report.write_metadata_json(str(tmp_path / "T_metadata.json"), res,
+                                   {"width": 1920, "height": 1080, "fps": 30.0, "frame_count": 3, "duration_seconds": 0.1},
+                                   {"model": "vmaf_v0.6.1", "pool_method": "mean"}, "T")
+    m = json.load(open(p))
+    assert m["vmaf_score"] == 91.0 and m["json_result"] == "T_vmaf.json" and m["psnr_file"] == "T_psnr.txt"
+    assert m["ssim_file"] is None and m["video_details"]["resolution"] == "1920x1080"
+    assert m["analysis_settings"]["model"] == "vmaf_v0.6.1" and "os" in m["system_info"]
