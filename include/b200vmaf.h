@@ -122,6 +122,8 @@ int  bv_flush(bv_ctx *);                 /* launch the partial group and drain e
 int  bv_kick(bv_ctx *);                  /* launch the partial group now, without draining: lets a caller start the
                                             GPU on the first few frames of a clip instead of waiting for a full group */
 int64_t bv_frames_done(bv_ctx *);        /* frames whose features are ready (non-blocking)      */
+int  bv_batch_frames(bv_ctx *);          /* frame pairs per launch group of this ctx (opts.batch_frames, or the auto
+                                            choice: 32 up to 1440p, 16 at 2160p)                                */
 /* Copy out features of `count` frames starting at submission ordinal `first` (0-based, in
  * submission order incl. lead-in frames); blocks until they are ready. */
 int  bv_fetch(bv_ctx *, int64_t first, int64_t count, bv_frame_features *out);

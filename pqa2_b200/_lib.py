@@ -67,7 +67,7 @@ EXPORTS = (
     "bv_abi_version", "bv_device_count", "bv_create", "bv_destroy", "bv_last_error", "bv_pinned_alloc",
     "bv_pinned_free", "bv_device_alloc", "bv_device_free", "bv_device_upload", "bv_sizeof_frame_features",
     "bv_submit", "bv_submit_device", "bv_wait_uploads", "bv_flush", "bv_frames_done", "bv_fetch", "bv_cancel",
-    "bv_reset", "bv_kick",
+    "bv_reset", "bv_kick", "bv_batch_frames",
     "bv_kernel_launches", "bv_set_profiling", "bv_kernel_slots", "bv_kernel_name", "bv_kernel_ms", "bv_kernel_count",
     "bv_timer_mark", "bv_timer_elapsed_ms",
     "bv_model_create", "bv_model_free", "bv_predict", "bv_predict_device", "bv_luma_stats_device",
@@ -119,6 +119,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.bv_cancel.argtypes = [vp]
     L.bv_reset.argtypes = [vp]
     L.bv_kick.argtypes = [vp]
+    L.bv_batch_frames.argtypes = [vp]
+    L.bv_batch_frames.restype = i
     L.bv_kernel_launches.argtypes = [vp]
     L.bv_kernel_launches.restype = i64
     L.bv_set_profiling.argtypes = [vp, i]

@@ -497,7 +497,15 @@ bv_ctx *bv_create(int device, int width, int height, int bpc, int chroma, unsign
         if (d.adm_ref_display_height <= 0) d.adm_ref_display_height = 1080;
     }
     c->opts = d;
-    c->B = d.batch_frames > 0 ? (d.batch_frames > BV_MAX_BATCH ? BV_MAX_BATCH : d.batch_frames) : BV_MAX_BATCH;
+    if (d.batch_frames > 0) c->B = d.batch_frames > BV_MAX_BATCH ? BV_MAX_BATCH : d.batch_frames;
+    else {
+        // auto: twice the work of a launch group of 32 1080p frames, capped at 32 frames (enough tiles to fill 148
+        // SMs at every pyramid level, launch gaps amortised).  Larger pictures reach it with fewer frames -- 2160p: 16
+        // -- which bounds the per-context footprint and the pipeline fill/drain time (one group).
+        const double px = (double)width * height;
+        int b = (int)(2.0 * BV_MAX_BATCH * (1920.0 * 1080.0) / px + 0.5);
+        c->B = b < 4 ? 4 : (b > BV_MAX_BATCH ? BV_MAX_BATCH : b);
+    }
     if (alloc_ctx(c) != 0) {
         g_create_error = c->err;
         bv_destroy(c);
@@ -616,6 +624,8 @@ int bv_kick(bv_ctx *c)
 }
 
 int64_t bv_frames_done(bv_ctx *c) { return c ? c->ready.load() : 0; }
+
+int bv_batch_frames(bv_ctx *c) { return c ? c->B : 0; }
 
 int bv_reset(bv_ctx *c)
 {

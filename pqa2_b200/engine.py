@@ -159,7 +159,7 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
         else:
             fx.reset()
         ctx_holder.append(fx)
-        B = opt.batch_frames or L.BV_MAX_BATCH
+        B = fx.batch_frames
         zero_copy = bool(getattr(handle, "zero_copy", False))
         ring = None
         if not zero_copy:
@@ -187,8 +187,12 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
                 flags |= L.FRAME_SKIP_SPATIAL
             fx.submit(i, rp, dp, flags)
             ordinal += 1
-            if ordinal == _FIRST_KICK and B > _FIRST_KICK:
-                fx.kick()                   # start the GPU on a short first group: the pipeline fills 4x sooner
+            left = end - 1 - i              # frames still to submit
+            if (ordinal == min(_FIRST_KICK, B // 2) and B > 1) or (left >= 2 and left in (B // 2, B // 4)):
+                # start the GPU on a short first group (the pipeline fills sooner) and split the tail into halving
+                # groups: when uploads are the bottleneck (2160p over PCIe) the drain after the last upload is the
+                # compute time of the LAST launch only
+                fx.kick()
             if progress:
                 progress(1)
         fx.flush()

@@ -138,6 +138,11 @@ class FeatureExtractor:
         return int(self.lib.bv_frames_done(self._ctx))
 
     @property
+    def batch_frames(self) -> int:
+        """Frame pairs per launch group of this context (the auto choice when none was requested)."""
+        return int(self.lib.bv_batch_frames(self._ctx))
+
+    @property
     def kernel_launches(self) -> int:
         return int(self.lib.bv_kernel_launches(self._ctx))
 
