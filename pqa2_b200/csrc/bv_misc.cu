@@ -28,24 +28,36 @@ sse_kernel(BvBatch batch, BvPlane ref, BvPlane dis, int w, int h, unsigned long 
         size_t done = 0;
         if (vec_ok) {
             const size_t nv = row_bytes / 16;
-            for (size_t v = lane; v < nv; v += 32) {
-                const uint4 x = __ldg(reinterpret_cast<const uint4 *>(a) + v);
-                const uint4 y = __ldg(reinterpret_cast<const uint4 *>(b) + v);
-                const unsigned xs[4] = { x.x, x.y, x.z, x.w }, ys[4] = { y.x, y.y, y.z, y.w };
-                if (sizeof(T) == 1) {
-                    unsigned s = 0;
+            // 4 x 2 independent 16-byte loads in flight per lane (HBM-bound: bytes in flight are what matters)
+            constexpr int U = 4;
+            for (size_t v0 = lane; v0 < nv; v0 += 32 * U) {
+                uint4 xv[U], yv[U];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const unsigned d = __vabsdiffu4(xs[q], ys[q]);
-                        s = __dp4a(d, d, s);
-                    }
-                    acc += s;
-                } else {
+                for (int u = 0; u < U; ++u) {
+                    const size_t v = v0 + 32 * u;
+                    if (v < nv) {
+                        xv[u] = __ldg(reinterpret_cast<const uint4 *>(a) + v);
+                        yv[u] = __ldg(reinterpret_cast<const uint4 *>(b) + v);
+                    } else { xv[u] = make_uint4(0, 0, 0, 0); yv[u] = xv[u]; }
+                }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const unsigned d = __vabsdiffu2(xs[q], ys[q]);
-                        const unsigned long long lo = d & 0xffffu, hi = d >> 16;
-                        acc += lo * lo + hi * hi;
+                for (int u = 0; u < U; ++u) {
+                    const unsigned xs[4] = { xv[u].x, xv[u].y, xv[u].z, xv[u].w }, ys[4] = { yv[u].x, yv[u].y, yv[u].z, yv[u].w };
+                    if (sizeof(T) == 1) {
+                        unsigned s = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const unsigned d = __vabsdiffu4(xs[q], ys[q]);
+                            s = __dp4a(d, d, s);
+                        }
+                        acc += s;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const unsigned d = __vabsdiffu2(xs[q], ys[q]);
+                            const unsigned long long lo = d & 0xffffu, hi = d >> 16;
+                            acc += lo * lo + hi * hi;
+                        }
                     }
                 }
             }
@@ -261,8 +273,10 @@ void bv_launch_ffssim(const BvBatch &b, BvPlane ref, BvPlane dis, int bpc, int w
 void bv_launch_sse(const BvBatch &b, BvPlane ref, BvPlane dis, int bpc, int w, int h, int plane_idx,
                    unsigned long long *raw, const BvLaunch &L)
 {
+    // one wave of 8 CTAs per SM over the whole group (a warp streams whole rows)
     int gx = (h + 7) / 8;
-    if (gx > 148) gx = 148;
+    const int wave = (148 * 8 + b.n - 1) / b.n;
+    if (gx > wave) gx = wave;
     dim3 grid(gx, b.n);
     bv_prof_begin(L, BVK_SSE_Y + plane_idx);
     if (bpc == 8) sse_kernel<uint8_t><<<grid, 256, 0, L.st>>>(b, ref, dis, w, h, raw, BV_RAW_SSE + plane_idx);
