@@ -162,6 +162,9 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
     unsigned long long *s_row = reinterpret_cast<unsigned long long *>(s_cc + AT_H * AT_W);   // [AT_H][6]
     Stage *s_in = reinterpret_cast<Stage *>(s_row + AT_H * 6);                       // [2][AN_R][AN_P]
 
+    __shared__ int4 s_rk[AP_H], s_ck[AP_W];          // staged row / column of the 4 DWT taps of a band row / column
+    __shared__ int2 s_rinfo[AP_H], s_cinfo[AP_W];    // (mirrored band index, region flags: 1 valid, 2 in image, 4 decouple region, 8 core)
+
     const int in_w = a.sp.in_w, in_h = a.sp.in_h, ow = a.sp.w, oh = a.sp.h;
     const int tid = threadIdx.x;
     V4 pre_r[NPF], pre_d[NPF];
@@ -193,6 +196,35 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
     const int cx0 = 2 * tx0 - 4, ry0 = 2 * ty0 - 3;
 
     if (tid < AT_H * 6) s_row[tid] = 0ull;
+    // Per-tile index tables: the MIRROR / clamp arithmetic of the two DWT passes and the region tests depend only on
+    // the band row or the band column, so they are evaluated once per row / column here instead of once per tap of
+    // every position (ncu: that arithmetic was ~25 % of the executed instructions).
+    const int left = a.sp.left, top = a.sp.top, right = a.sp.right, bottom = a.sp.bottom;
+    if (tid < AP_H) {
+        const int r = tid, bi_raw = ty0 - 1 + r;
+        const int bi = bv_mirror(clampi(bi_raw, -1, oh), oh);
+        int4 rk;
+        rk.x = clampi(bv_mirror(2 * bi - 1, in_h) - ry0, 0, AN_R - 1);
+        rk.y = clampi(bv_mirror(2 * bi, in_h) - ry0, 0, AN_R - 1);
+        rk.z = clampi(bv_mirror(2 * bi + 1, in_h) - ry0, 0, AN_R - 1);
+        rk.w = clampi(bv_mirror(2 * bi + 2, in_h) - ry0, 0, AN_R - 1);
+        s_rk[r] = rk;
+        const int gt = max(top - 1, 0), gb = min(bottom + 1, oh);
+        s_rinfo[r] = make_int2(bi, (bi_raw >= -1 && bi_raw <= oh ? 1 : 0) | (bi_raw < oh ? 2 : 0) |
+                                   (bi >= gt && bi < gb ? 4 : 0) | (bi >= top && bi < bottom ? 8 : 0));
+    } else if (tid >= 32 && tid < 32 + AP_W) {
+        const int c = tid - 32, bj_raw = tx0 - 1 + c;
+        const int bj = bv_mirror(clampi(bj_raw, -1, ow), ow);
+        int4 ck;
+        ck.x = clampi(bv_mirror(2 * bj - 1, in_w) - cx0, 0, AN_C - 1);
+        ck.y = clampi(bv_mirror(2 * bj, in_w) - cx0, 0, AN_C - 1);
+        ck.z = clampi(bv_mirror(2 * bj + 1, in_w) - cx0, 0, AN_C - 1);
+        ck.w = clampi(bv_mirror(2 * bj + 2, in_w) - cx0, 0, AN_C - 1);
+        s_ck[c] = ck;
+        const int gl = max(left - 1, 0), gr = min(right + 1, ow);
+        s_cinfo[c] = make_int2(bj, (bj_raw >= -1 && bj_raw <= ow ? 1 : 0) | (bj_raw < ow ? 2 : 0) |
+                                   (bj >= gl && bj < gr ? 4 : 0) | (bj >= left && bj < right ? 8 : 0));
+    }
 
     // ---- phase A: registers -> shared (MIRROR was resolved by the loads) ----
     if (!skip) {
@@ -216,10 +248,8 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
     // ---- phase B: vertical DWT pass: lo/hi of ref and dis for every band row of the halo tile ----
     for (int idx = tid; idx < AP_H * AN_C; idx += AT_THREADS) {
         const int r = idx / AN_C, c = idx - r * AN_C;
-        const int bi = bv_mirror(clampi(ty0 - 1 + r, -1, oh), oh);
-        int rk[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) rk[k] = clampi(bv_mirror(2 * bi - 1 + k, in_h) - ry0, 0, AN_R - 1);
+        const int4 rk4 = s_rk[r];
+        const int rk[4] = { rk4.x, rk4.y, rk4.z, rk4.w };
         VT out;
         if (SCALE == 0) {
             const int add_v = 1 << (a.bpc - 1);
@@ -251,8 +281,6 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
     __syncthreads();
 
     // ---- phase C: horizontal DWT pass + decouple + CSF for every position (interior first) ----
-    const int left = a.sp.left, top = a.sp.top, right = a.sp.right, bottom = a.sp.bottom;
-    const int gl = max(left - 1, 0), gt = max(top - 1, 0), gr = min(right + 1, ow), gb = min(bottom + 1, oh);
 #pragma unroll 1
     for (int p = tid; p < AT_H * AT_W + A_RING; p += AT_THREADS) {
         const bool interior = p < AT_H * AT_W;         // warp-uniform (AT_H*AT_W is a multiple of 32)
@@ -265,20 +293,18 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
             else if (q < 2 * AP_W) { r = AP_H - 1; c = q - AP_W; }
             else { r = 1 + ((q - 2 * AP_W) >> 1); c = ((q - 2 * AP_W) & 1) ? AP_W - 1 : 0; }
         }
-        const int bi_raw = ty0 - 1 + r, bj_raw = tx0 - 1 + c;
-        const bool valid = bi_raw >= -1 && bi_raw <= oh && bj_raw >= -1 && bj_raw <= ow;
-        const int bi = bv_mirror(clampi(bi_raw, -1, oh), oh), bj = bv_mirror(clampi(bj_raw, -1, ow), ow);
-        const bool in_img = bi_raw < oh && bj_raw < ow;            // interior positions only
-        const bool in_g = valid && bi >= gt && bi < gb && bj >= gl && bj < gr;
-        const bool core = interior && in_img && bi >= top && bi < bottom && bj >= left && bj < right;
+        const int2 ri = s_rinfo[r], ci = s_cinfo[c];
+        const int bi = ri.x, bj = ci.x, fl = ri.y & ci.y;
+        const bool in_img = fl & 2;                                // interior positions only
+        const bool in_g = (fl & 5) == 5;
+        const bool core = interior && (fl & 10) == 10;
 
         unsigned long long dsum[3] = { 0ull, 0ull, 0ull };
         int cfsum = 0;
         if (in_g || (interior && in_img && SCALE < 3)) {
-            VT tv[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                tv[k] = s_v[r * AN_P + clampi(bv_mirror(2 * bj - 1 + k, in_w) - cx0, 0, AN_C - 1)];
+            const int4 ck = s_ck[c];
+            const VT *vrow = s_v + r * AN_P;
+            const VT tv[4] = { vrow[ck.x], vrow[ck.y], vrow[ck.z], vrow[ck.w] };
             if (SCALE < 3 && interior && in_img) {
                 Out ar, ad;
                 if (SCALE == 0) {
@@ -357,8 +383,7 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
 #pragma unroll 1
     for (int p = tid; p < AT_H * AT_W; p += AT_THREADS) {
         const int r = p / AT_W + 1, c = p % AT_W + 1;
-        const int bi = ty0 - 1 + r, bj = tx0 - 1 + c;
-        const bool core = bi >= top && bi < bottom && bj >= left && bj < right && bi < oh && bj < ow;
+        const bool core = ((s_rinfo[r].y & s_cinfo[c].y) & 10) == 10;
         if (!__any_sync(0xffffffffu, core)) continue;
         long long val[3] = { 0, 0, 0 };
         if (core) {
