@@ -159,8 +159,8 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
     int *s_cf = reinterpret_cast<int *>(smem + sizeof(VT) * AP_H * AN_P);            // [AP_H][AP_W]
     int *s_x = s_cf + AP_H * AP_W;                                                   // [3][AT_H*AT_W]
     int *s_cc = s_x + 3 * AT_H * AT_W;                                               // [AT_H*AT_W]
-    unsigned long long *s_row = reinterpret_cast<unsigned long long *>(s_cc + AT_H * AT_W);   // [AT_H][6]
-    Stage *s_in = reinterpret_cast<Stage *>(s_row + AT_H * 6);                       // [2][AN_R][AN_P]
+    unsigned long long *s_row = reinterpret_cast<unsigned long long *>(s_cc + AT_H * AT_W);   // [AT_H][2 half rows][6]
+    Stage *s_in = reinterpret_cast<Stage *>(s_row + AT_H * 12);                      // [2][AN_R][AN_P]
 
     __shared__ int4 s_rk[AP_H], s_ck[AP_W];          // staged row / column of the 4 DWT taps of a band row / column
     __shared__ int2 s_rinfo[AP_H], s_cinfo[AP_W];    // (mirrored band index, region flags: 1 valid, 2 in image, 4 decouple region, 8 core)
@@ -195,7 +195,7 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
     const int tx0 = (rem % tiles_x) * AT_W, ty0 = (rem / tiles_x) * AT_H;
     const int cx0 = 2 * tx0 - 4, ry0 = 2 * ty0 - 3;
 
-    if (tid < AT_H * 6) s_row[tid] = 0ull;
+    if (tid < AT_H * 12) s_row[tid] = 0ull;
     // Per-tile index tables: the MIRROR / clamp arithmetic of the two DWT passes and the region tests depend only on
     // the band row or the band column, so they are evaluated once per row / column here instead of once per tap of
     // every position (ncu: that arithmetic was ~25 % of the executed instructions).
@@ -372,8 +372,9 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
             // a warp covers 32 consecutive interior columns of one tile row
 #pragma unroll
             for (int b = 0; b < 3; ++b) {
-                const unsigned long long s = bv_warp_sum(dsum[b]);
-                if ((tid & 31) == 0 && s) atomicAdd(&s_row[(r - 1) * 6 + 3 + b], s);
+                const unsigned long long s = (unsigned long long)bv_warp_sum_redux((long long)dsum[b]);      // < 2^56
+                // a (tile row, half row) pair belongs to exactly one warp and one trip: plain store, no atomic
+                if ((tid & 31) == 0) s_row[((r - 1) * 2 + (c > 32)) * 6 + 3 + b] = s;
             }
         }
     }
@@ -403,14 +404,14 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
         }
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            const long long s = bv_warp_sum(val[b]);
-            if ((tid & 31) == 0 && s) atomicAdd(&s_row[(r - 1) * 6 + b], (unsigned long long)s);
+            const long long s = bv_warp_sum_redux(val[b]);                                                // 0 <= val < 2^57
+            if ((tid & 31) == 0) s_row[((r - 1) * 2 + (c > 32)) * 6 + b] = (unsigned long long)s;
         }
     }
     __syncthreads();
     if (tid < AT_H * 6) {
         const int rr = tid / 6, k = tid - rr * 6;
-        const unsigned long long s = s_row[tid];
+        const unsigned long long s = s_row[rr * 12 + k] + s_row[rr * 12 + 6 + k];
         if (s && ty0 + rr < oh)
             atomicAdd(a.rows + (size_t)f * a.rows_frame_stride + a.rows_offset + (size_t)(ty0 + rr) * 6 + k, s);
     }
@@ -420,7 +421,7 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
 template <int SCALE> size_t adm_smem()
 {
     return sizeof(typename AdmTypes<SCALE>::V) * AP_H * AN_P + sizeof(int) * (AP_H * AP_W + 4 * AT_H * AT_W) +
-           sizeof(unsigned long long) * AT_H * 6 + sizeof(typename AdmTypes<SCALE>::Stage) * 2 * AN_R * AN_P;
+           sizeof(unsigned long long) * AT_H * 12 + sizeof(typename AdmTypes<SCALE>::Stage) * 2 * AN_R * AN_P;
 }
 
 struct AdmFinishArgs {

@@ -43,6 +43,16 @@ __device__ __forceinline__ unsigned long long bv_warp_sum(unsigned long long v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// 64-bit warp sum through three 32-bit hardware reductions (REDUX instead of 10 SHFL + 10 adds):
+// v = c2 * 2^44 + c1 * 2^22 + c0 with 22-bit c0, c1 and a signed c2; every chunk sum fits 32 bits for |v| < 2^62.
+__device__ __forceinline__ long long bv_warp_sum_redux(long long v)
+{
+    const unsigned c0 = (unsigned)v & 0x3fffffu, c1 = (unsigned)(v >> 22) & 0x3fffffu;
+    const int c2 = (int)(v >> 44);
+    const unsigned s0 = __reduce_add_sync(0xffffffffu, c0), s1 = __reduce_add_sync(0xffffffffu, c1);
+    const int s2 = __reduce_add_sync(0xffffffffu, c2);
+    return (long long)s0 + ((long long)s1 << 22) + ((long long)s2 << 44);
+}
 __device__ __forceinline__ int bv_warp_sum(int v)
 {
 #pragma unroll
