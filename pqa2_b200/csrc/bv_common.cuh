@@ -62,7 +62,8 @@ __device__ __forceinline__ int bv_warp_sum(int v)
 
 // Sum N per-thread 64-bit values over the block and atomically add them to dst[0..N).
 // scratch: N * 32 long longs of shared memory.
-template <int N>
+// REDUX: the caller guarantees |v| < 2^62 for every partial sum (then the warp sums use bv_warp_sum_redux).
+template <int N, bool REDUX = false>
 __device__ __forceinline__ void bv_block_accumulate(const long long (&v)[N], long long *scratch,
                                                     unsigned long long *dst)
 {
@@ -71,7 +72,7 @@ __device__ __forceinline__ void bv_block_accumulate(const long long (&v)[N], lon
     const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        long long s = bv_warp_sum(v[k]);
+        long long s = REDUX ? bv_warp_sum_redux(v[k]) : bv_warp_sum(v[k]);
         if (lane == 0) scratch[k * 32 + warp] = s;
     }
     __syncthreads();
@@ -79,7 +80,7 @@ __device__ __forceinline__ void bv_block_accumulate(const long long (&v)[N], lon
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             long long s = lane < nwarps ? scratch[k * 32 + lane] : 0;
-            s = bv_warp_sum(s);
+            s = REDUX ? bv_warp_sum_redux(s) : bv_warp_sum(s);
             if (lane == 0 && s != 0) atomicAdd(dst + k, (unsigned long long)s);
         }
     }
