@@ -406,6 +406,17 @@ def main() -> int:
                     "share_of_step": kernels[top]["ms_per_launch"] / tot_ms,
                     "pipeline_floor_gbps": 2 * plane * value / world / 1e9,
                     "pipeline_floor_frac": 2 * plane * value / world / 1e9 / peak}
+        # The stencil kernels sit on the instruction-issue roof, not on HBM: report that roof too.
+        # Executed warp instructions per launch come from the committed ncu capture of this kernel; the rate is
+        # measured live (CUDA-event launch time); peak = SMs x 4 schedulers x 1 warp instruction per clock.
+        if tr and tr.get("warp_inst") and clocks.get("sm_mhz"):
+            wi = tr["warp_inst"] * B / tr["frames"]
+            peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
+            roofline["issue"] = {"warp_instructions_per_launch": wi,
+                                 "achieved_gwarp_inst_s": wi / (kernels[top]["ms_per_launch"] * 1e-3) / 1e9,
+                                 "peak_gwarp_inst_s": peak_issue / 1e9,
+                                 "frac": wi / (kernels[top]["ms_per_launch"] * 1e-3) / peak_issue,
+                                 "thread_instructions_per_pixel": wi * 32 / (B * w * h)}
     fx.close()
 
     # ---- end to end through the public engine call: pinned host frames in, scores out

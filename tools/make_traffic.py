@@ -28,6 +28,7 @@ KEYS = [("us", "gpu__time_duration.sum"), ("dram_read_MB", "dram__bytes_read.sum
         ("alu_pipe_pct", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
         ("fp64_pipe_pct", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
         ("warps_active_pct", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+        ("warp_inst", "smsp__inst_executed.sum"),
         ("regs", "launch__registers_per_thread"),
         ("stall_long_sb", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
         ("stall_wait", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"),
@@ -60,17 +61,20 @@ def load(path, wname, frames):
                 continue
             e[k] = round(v, 3)
         e["bytes"] = int(round((e.get("dram_read_MB", 0) + e.get("dram_write_MB", 0)) * 1e6))
-        e["source"] = f"ncu --set full --clock-control none, {os.path.basename(path)} (profiles/r01_ncu_full_{wname}_v3.md)"
+        e["source"] = f"ncu --set full --clock-control none, {os.path.basename(path)} (profiles/r01_ncu_full_{wname}_{VER}.md)"
         e["pipe_note"] = (f"issue slots {e.get('issue_pct')} % active, FMA pipe {e.get('fma_pipe_pct')} %, ALU pipe "
                           f"{e.get('alu_pipe_pct')} %, FP64 pipe {e.get('fp64_pipe_pct')} %: bound by instruction issue, not by HBM")
         out[nm] = e
     return out
 
 
+VER = sys.argv[1] if len(sys.argv) > 1 else "v3"
+
+
 def main():
     frames = 32
     traffic = {}
-    for wname, path in (("1080p-float", "gpurun_out/raw_float_v3.csv"), ("1080p-int", "gpurun_out/raw_int_v3.csv")):
+    for wname, path in (("1080p-float", f"gpurun_out/raw_float_{VER}.csv"), ("1080p-int", f"gpurun_out/raw_int_{VER}.csv")):
         p = os.path.join(ROOT, path)
         if not os.path.exists(p):
             continue
@@ -83,7 +87,7 @@ def main():
         for nm in ORDER[wname]:
             if nm in t:
                 lines.append(" | ".join([nm] + [str(t[nm].get(k, "")) for k, _ in KEYS]))
-        open(os.path.join(ROOT, "profiles", f"r01_ncu_full_{wname}_v3.md"), "w").write("\n".join(lines) + "\n")
+        open(os.path.join(ROOT, "profiles", f"r01_ncu_full_{wname}_{VER}.md"), "w").write("\n".join(lines) + "\n")
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "r01_traffic.json"), "w"), indent=1)
     print({w: len(t) for w, t in traffic.items()})
 
