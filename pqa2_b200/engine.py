@@ -348,7 +348,17 @@ def percentile(sorted_vals, p: float) -> float:
     return sorted_vals[lo] + (sorted_vals[hi] - sorted_vals[lo]) * (pos - lo)
 
 
-def _build_frames_block(rows: Rows, model: VmafModel, opt: EngineOptions, device: int | None) -> list:
+def _pool_column(col: np.ndarray) -> dict:
+    """report.pool() on a column: the same left-to-right double sums (np.cumsum is strictly sequential)."""
+    n = len(col)
+    if n == 0:
+        return {"min": 0.0, "max": 0.0, "mean": 0.0, "harmonic_mean": 0.0}
+    return {"min": float(col.min()), "max": float(col.max()), "mean": float(np.cumsum(col)[-1]) / n,
+            "harmonic_mean": n / float(np.cumsum(1.0 / (col + 1.0))[-1]) - 1.0}
+
+
+def _build_frames_block(rows: Rows, model: VmafModel, opt: EngineOptions, device: int | None,
+                        pooled_out: dict | None = None) -> list:
     """build_frames() on a Rows block: whole columns at a time (the per-row dict path costs ~50 us/frame in
     Python, which at several thousand frames/s is as much as the GPU work itself)."""
     a = rows.arr
@@ -405,13 +415,24 @@ def _build_frames_block(rows: Rows, model: VmafModel, opt: EngineOptions, device
             fr["metrics"]["vmaf"] = vmaf[j]
             if boots is not None:
                 fr["metrics"].update(_bootstrap_metrics(model, boots[j], opt))
+        if pooled_out is not None and boots is None:
+            # pooled_metrics straight from the columns (the per-frame dict walk of report.pooled_metrics costs ~1 ms
+            # per 512 frames -- as much as a third of a launch group of GPU work)
+            tab = np.asarray(table, np.float64)
+            pooled = {nm: _pool_column(tab[:, k]) for k, nm in enumerate(names)}
+            for nm, vals, ok in extras:
+                okm = np.asarray(ok, bool)
+                if okm.any():
+                    pooled[nm] = _pool_column(np.asarray(vals, np.float64)[okm])
+            pooled["vmaf"] = _pool_column(np.asarray(vmaf, np.float64))
+            pooled_out["pooled"] = pooled
     return frames
 
 
-def build_frames(rows, model: VmafModel, opt: EngineOptions, device: int | None) -> list:
+def build_frames(rows, model: VmafModel, opt: EngineOptions, device: int | None, pooled_out: dict | None = None) -> list:
     """Per-frame feature rows -> libvmaf 'frames' list (metric names of SURVEY.md Appendix A.8)."""
     if isinstance(rows, Rows):
-        return _build_frames_block(rows, model, opt, device)
+        return _build_frames_block(rows, model, opt, device, pooled_out)
     is_f = model.is_float
     pre = "" if is_f else "integer_"
     vs, as_ = _egl_suffix(model.vif_enhn_gain_limit), _egl_suffix(model.adm_enhn_gain_limit)
@@ -548,11 +569,12 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
     if first > 0:
         # a sub-range does not know the frame before it: libvmaf would have started at index 0 too
         pass
-    frames = build_frames(rows_used, model, opt, devices[0])
+    pooled_out: dict = {}
+    frames = build_frames(rows_used, model, opt, devices[0], pooled_out)
     for fr in frames:
         fr["frameNum"] += first
     dt = time.perf_counter() - t0
-    pooled = report.pooled_metrics(frames)
+    pooled = pooled_out.get("pooled") or report.pooled_metrics(frames)
     return {"version": report.VERSION, "fps": n / dt if dt > 0 else 0.0, "frames": frames,
             "pooled_metrics": pooled, "aggregate_metrics": {}, "rows": rows_used,
             "model": model.name, "elapsed_s": dt, "n_frames": n}

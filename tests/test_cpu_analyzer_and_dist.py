@@ -204,3 +204,14 @@ def test_libvmaf_filter_string_round_trip():
     legacy = O.parse_libvmaf_filter("libvmaf=log_fmt=json:log_path=/tmp/vmaf.json:psnr=1:ssim=1:model_path=/m/vmaf_v0.6.1.json")
     assert legacy["model"] == "/m/vmaf_v0.6.1.json" and legacy["options"].psnr and legacy["options"].ssim
     assert M.resolve_model(O.parse_libvmaf_filter("libvmaf=model=version=vmaf_4k_v0.6.1")["model"]).name == "vmaf_4k_v0.6.1"
+
+
+def test_column_pooling_equals_the_per_frame_walk():
+    """engine._pool_column (numpy, sequential cumsum) == report.pool (libvmaf's left-to-right double sums), bit for bit."""
+    import numpy as np
+    from pqa2_b200 import engine, report
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 17, 513):
+        col = rng.uniform(0.0, 100.0, n)
+        assert engine._pool_column(col) == report.pool(col.tolist())
+    assert engine._pool_column(np.zeros(0)) == report.pool([])

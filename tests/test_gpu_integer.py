@@ -265,6 +265,8 @@ def test_shard_invariance_and_batch_of_clips():
     one = engine.analyze(src, model, engine.EngineOptions(devices=(0,)))
     three = engine.analyze(src, model, engine.EngineOptions(devices=(0, 0, 0)))
     assert [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in three["frames"]]
+    from pqa2_b200 import report
+    assert one["pooled_metrics"] == report.pooled_metrics(one["frames"])          # column pooling == per-frame walk
     fmodel = M.resolve_model("vmaf_float_v0.6.1")
     fone = engine.analyze(src, fmodel, engine.EngineOptions(devices=(0,)))
     fthree = engine.analyze(src, fmodel, engine.EngineOptions(devices=(0, 0, 0)))
