@@ -167,6 +167,9 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
                 [([pinned_empty(s, dtype) for s in shapes], [pinned_empty(s, dtype) for s in shapes]) for _ in range(2 * B)]
         lead = 1 if start > 0 else 0
         ordinal = 0
+        # pictures large enough for a reduced group size are upload-bound over PCIe: only there does a short last
+        # launch shorten the call; at <= 1440p the GPU is the bottleneck and short groups would only run less efficiently
+        tail_split = B < L.BV_MAX_BATCH
         for i in range(start - lead, end):
             if cancel.is_set():
                 fx.cancel()
@@ -188,7 +191,7 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
             fx.submit(i, rp, dp, flags)
             ordinal += 1
             left = end - 1 - i              # frames still to submit
-            if (ordinal == min(_FIRST_KICK, B // 2) and B > 1) or (left >= 2 and left in (B // 2, B // 4)):
+            if (ordinal == min(_FIRST_KICK, B // 2) and B > 1) or (tail_split and left >= 2 and left in (B // 2, B // 4)):
                 # start the GPU on a short first group (the pipeline fills sooner) and split the tail into halving
                 # groups: when uploads are the bottleneck (2160p over PCIe) the drain after the last upload is the
                 # compute time of the LAST launch only

@@ -356,3 +356,40 @@ def test_engine_subsample_and_cancel():
         assert sess.analyze(src, model, engine.EngineOptions(), cancel=ev) is None
         again = sess.analyze(src, model, engine.EngineOptions())
         assert [fr["metrics"] for fr in again["frames"]] == [fr["metrics"] for fr in full["frames"]]
+
+
+@pytest.mark.parametrize("w,h,bpc", [(1920, 1080, 8), (3840, 2160, 10)])
+def test_full_size_properties(w, h, bpc):
+    """Size-independent properties at the BASELINE.json picture sizes (the oracle needs minutes per 4K clip, so full-size
+    clips are checked through invariants): identical pair => vif ~ 1, adm2 ~ 1, psnr = 6 * bpc + 12; static clip =>
+    motion = 0; SSE symmetric under swapping ref and dis while motion follows the reference only; integer accumulators
+    identical however the frames are grouped (groups of 32/16 vs groups of 3) and sharded (1 vs 2 shards)."""
+    from pqa2_b200 import engine, model as M
+    feats = L.FEAT_VMAF_INT | L.FEAT_PSNR_Y
+    frames = [synth.frame_pair(9, f, w, h, bpc, chroma=False) for f in range(5)]
+    with FeatureExtractor(w, h, bpc, 0, feats) as fx:
+        for f in range(3):
+            fx.submit(f, frames[0][0], frames[0][0], L.FRAME_FIRST if f == 0 else 0)
+        same = fx.fetch()
+    for f in range(3):
+        assert same[f].motion == 0.0 and same[f].psnr_y == 6.0 * bpc + 12.0
+        assert abs(same[f].adm2 - 1.0) < 1e-4 and all(abs(same[f].vif_scale[s] - 1.0) < 1e-4 for s in range(4))
+
+    def run(pairs, batch):
+        with FeatureExtractor(w, h, bpc, 0, feats, batch_frames=batch) as fx:
+            for f, (a, b) in enumerate(pairs):
+                fx.submit(f, a, b, L.FRAME_FIRST if f == 0 else 0)
+            return [np.array(r.raw[:], dtype=np.int64) for r in fx.fetch()]
+
+    fwd = run(frames, 0)
+    assert all(np.array_equal(x, y) for x, y in zip(fwd, run(frames, 3)))             # grouping-invariant
+    swp = run([(d, r) for r, d in frames], 0)
+    for f in range(5):
+        assert fwd[f][L.RAW_SSE] == swp[f][L.RAW_SSE] and fwd[f][L.RAW_SSE] > 0       # SSE symmetric
+    assert [int(x[L.RAW_SAD]) for x in fwd[1:]] != [int(x[L.RAW_SAD]) for x in swp[1:]]   # motion reads the reference
+    src = engine.SynthSource(w, h, bpc, 5, seed=9, chroma=0)
+    mdl = M.resolve_model("vmaf_4k_v0.6.1" if w > 1920 else "vmaf_v0.6.1")
+    one = engine.analyze(src, mdl, engine.EngineOptions(devices=(0,)))
+    two = engine.analyze(src, mdl, engine.EngineOptions(devices=(0, 0)))
+    assert [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in two["frames"]]
+    assert all(0.0 <= fr["metrics"]["vmaf"] <= 100.0 for fr in one["frames"])
