@@ -187,6 +187,9 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
         }
     };
 
+    // per-(tile row, half row, band) sums: zeroed here once, then by the thread that consumes a slot at the end of a
+    // tile (the same thread reads and clears, so no other thread's clear can overtake the read)
+    if (tid < AT_H * 12) s_row[tid] = 0ull;
     int t = blockIdx.x;
     if (t < total_tiles) prefetch(t);
     for (; t < total_tiles; t += gridDim.x) {
@@ -195,7 +198,6 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
     const int tx0 = (rem % tiles_x) * AT_W, ty0 = (rem / tiles_x) * AT_H;
     const int cx0 = 2 * tx0 - 4, ry0 = 2 * ty0 - 3;
 
-    if (tid < AT_H * 12) s_row[tid] = 0ull;
     // Per-tile index tables: the MIRROR / clamp arithmetic of the two DWT passes and the region tests depend only on
     // the band row or the band column, so they are evaluated once per row / column here instead of once per tap of
     // every position (ncu: that arithmetic was ~25 % of the executed instructions).
@@ -412,6 +414,7 @@ adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int
     if (tid < AT_H * 6) {
         const int rr = tid / 6, k = tid - rr * 6;
         const unsigned long long s = s_row[rr * 12 + k] + s_row[rr * 12 + 6 + k];
+        s_row[rr * 12 + k] = 0ull; s_row[rr * 12 + 6 + k] = 0ull;
         if (s && ty0 + rr < oh)
             atomicAdd(a.rows + (size_t)f * a.rows_frame_stride + a.rows_offset + (size_t)(ty0 + rr) * 6 + k, s);
     }

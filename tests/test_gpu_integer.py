@@ -393,3 +393,21 @@ def test_full_size_properties(w, h, bpc):
     two = engine.analyze(src, mdl, engine.EngineOptions(devices=(0, 0)))
     assert [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in two["frames"]]
     assert all(0.0 <= fr["metrics"]["vmaf"] <= 100.0 for fr in one["frames"])
+
+
+def test_repeated_runs_are_bit_identical():
+    """Race detector: the persistent kernels hand shared-memory slots from tile to tile; any ordering hole shows up as
+    run-to-run differences.  Same 1080p clip four times through one context (integer accumulators and float sums)."""
+    w, h = 1920, 1080
+    frames = [synth.frame_pair(21, f, w, h, 8, chroma=False) for f in range(6)]
+    feats = L.FEAT_VMAF_INT | L.FEAT_VMAF_FLOAT | L.FEAT_PSNR_Y | L.FEAT_FLOAT_SSIM | L.FEAT_FLOAT_MS_SSIM
+    with FeatureExtractor(w, h, 8, 0, feats) as fx:
+        runs = []
+        for rep in range(4):
+            fx.reset()
+            for f, (a, b) in enumerate(frames):
+                fx.submit(f, a, b, L.FRAME_FIRST if f == 0 else 0)
+            out = fx.fetch()
+            runs.append([(tuple(r.raw[:]), tuple(r.f_vif_scale[:]), r.f_adm2, r.f_motion, r.float_ssim, r.float_ms_ssim)
+                         for r in out])
+    assert runs[0] == runs[1] == runs[2] == runs[3]
