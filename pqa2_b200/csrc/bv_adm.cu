@@ -145,7 +145,7 @@ template <> struct StageStore<int32_t> {
 // Persistent CTAs over (frame, tile) work items with register prefetch of the next tile's samples.
 template <int SCALE, typename TIn>
 __global__ void __launch_bounds__(AT_THREADS, 2)
-adm_scale_kernel(BvBatch batch, AdmArgs a, int tiles_x, int tiles_per_frame, int total_tiles)
+adm_scale_kernel(BvBatch batch, AdmArgs a, BvDiv tiles_x, BvDiv tiles_per_frame, int total_tiles)
 {
     using Stage = typename AdmTypes<SCALE>::Stage;
     using VT = typename AdmTypes<SCALE>::V;
@@ -475,7 +475,7 @@ void launch_scale(const BvBatch &b, const AdmArgs &a, cudaStream_t st)
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
     const int ctas = total < 2 * sms ? total : 2 * sms;
-    adm_scale_kernel<SCALE, TIn><<<ctas, AT_THREADS, smem, st>>>(b, a, tiles_x, tiles_per_frame, total);
+    adm_scale_kernel<SCALE, TIn><<<ctas, AT_THREADS, smem, st>>>(b, a, bv_make_div(tiles_x, tiles_per_frame), bv_make_div(tiles_per_frame, total), total);
 }
 
 float dwt_quant_step(int lambda, int theta, double view_dist, int display_h)
