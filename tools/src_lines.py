@@ -22,7 +22,7 @@ for r in rows[hi + 1:]:
     if len(r) <= ie: continue
     try: n = int(r[ie] or 0)
     except ValueError: continue
-    s = int(r[ss] or 0) if ss is not None and r[ss] else 0
+    s = int(r[ss]) if ss is not None and r[ss].isdigit() else 0
     if not r[0]: continue
     key = cur_file + ':' + r[0]
     agg[key][0] += n; agg[key][1] += s; agg[key][2] += 1
