@@ -190,6 +190,28 @@ __device__ __forceinline__ typename Px4<T>::V load_px4(const uint8_t *row, int g
     return Px4<T>::pack(__ldg(p + ix[0]), __ldg(p + ix[1]), __ldg(p + ix[2]), __ldg(p + ix[3]));
 }
 
+// Tile staging for the one-tile-per-CTA pyramid kernels (256 threads): a thread keeps its 4-sample column group and
+// walks down the rows, RPP rows per pass, so the column arithmetic is done once, the row loop has a fixed trip count and
+// all of a thread's loads are in flight before the first one is consumed.  ld(r, gc) -> V, st(r, gc, V).
+template <int IN_H, int GPR, typename V, typename LD, typename ST>
+__device__ __forceinline__ void bv_stage_tile(int tid, LD ld, ST st)
+{
+    constexpr int RPP = 256 / GPR, NP = (IN_H + RPP - 1) / RPP;
+    const int rr = tid / GPR, gc = tid - rr * GPR;
+    if (rr >= RPP) return;
+    V v[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int r = rr + i * RPP;
+        if (r < IN_H) v[i] = ld(r, gc);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int r = rr + i * RPP;
+        if (r < IN_H) st(r, gc, v[i]);
+    }
+}
+
 // ---- launch-parameter blocks (passed by value) --------------------------------------------------
 struct BvBatch {
     int n;                                  // frames in this launch group

@@ -12,7 +12,8 @@ namespace {
 // Tile = 128 x 32 outputs; the staged window starts 4 columns left of the tile so that 4-pixel vector
 // loads stay aligned.  Register-blocked: 8 outputs per item in both passes (12 inputs in registers).
 constexpr int MB_TW = 128, MB_TH = 32, MB_R = 2;
-constexpr int MB_IN_W = MB_TW + 8, MB_IN_H = MB_TH + 2 * MB_R, MB_G = MB_IN_W / 4, MB_P = MB_IN_W + 2, MB_O = 8;
+constexpr int MB_IN_W = MB_TW + 8, MB_IN_H = MB_TH + 2 * MB_R, MB_G = MB_IN_W / 4, MB_O = 8;
+constexpr int MB_P = MB_IN_W;            // u16 pitch of the staged tile: 8-byte rows (one 8-byte store per group; only read column-per-lane)
 constexpr int MB_VP = MB_IN_W + 1;       // odd u32 pitch of the vertical-pass plane
 
 __constant__ unsigned c_motion_filter[5] = { 3571, 16004, 26386, 16004, 3571 };
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(256)
 motion_blur_kernel(BvBatch batch, BvPlane src, int bpc, int w, int h, uint16_t *__restrict__ blur,
                    size_t blur_frame_elems, int vec_ok)
 {
-    __shared__ uint16_t s_in[MB_IN_H * MB_P];
+    __shared__ __align__(16) uint16_t s_in[MB_IN_H * MB_P];
     __shared__ unsigned s_v[MB_TH * MB_VP];
 
     const int f = blockIdx.z;
@@ -30,14 +31,17 @@ motion_blur_kernel(BvBatch batch, BvPlane src, int bpc, int w, int h, uint16_t *
     const int x0 = blockIdx.x * MB_TW - 4, y0 = blockIdx.y * MB_TH - MB_R;
     const int tid = threadIdx.x;
 
-    for (int g = tid; g < MB_IN_H * MB_G; g += 256) {
-        const int r = g / MB_G, gc = g - r * MB_G;
-        const int gy = bv_mirror(min(y0 + r, h + MB_R - 1), h);
-        unsigned u[4];
-        Px4<T>::raw(load_px4<T>(img + (size_t)gy * src.pitch, x0 + 4 * gc, w, w + MB_R - 1, vec_ok), u);
-        unsigned *p = reinterpret_cast<unsigned *>(s_in + r * MB_P + 4 * gc);
-        p[0] = u[0] | (u[1] << 16); p[1] = u[2] | (u[3] << 16);
-    }
+    using V4 = typename Px4<T>::V;
+    bv_stage_tile<MB_IN_H, MB_G, V4>(tid,
+        [&](int r, int gc) {
+            const int gy = bv_mirror(min(y0 + r, h + MB_R - 1), h);
+            return load_px4<T>(img + (size_t)gy * src.pitch, x0 + 4 * gc, w, w + MB_R - 1, vec_ok);
+        },
+        [&](int r, int gc, V4 v) {
+            unsigned u[4];
+            Px4<T>::raw(v, u);
+            *reinterpret_cast<uint2 *>(s_in + r * MB_P + 4 * gc) = make_uint2(u[0] | (u[1] << 16), u[2] | (u[3] << 16));
+        });
     __syncthreads();
 
     const unsigned add_v = 1u << (bpc - 1);
