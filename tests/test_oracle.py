@@ -94,3 +94,32 @@ def test_integer_and_float_extractors_agree_roughly():
     for s in range(4):
         assert abs(v["score"][s] - fl[f"vif_scale{s}"]) < 5e-3
     assert abs(a["adm2"] - fl["adm2"]) < 5e-3
+
+
+def test_oracle_psnr_and_ssim_against_independent_implementations():
+    """Two of the oracle's metrics have textbook definitions that other libraries in this image implement independently:
+    PSNR (cv2.PSNR) and single-scale SSIM with the 11x11 sigma-1.5 Gaussian window over the valid region (Wang et al.
+    2004, restated here with scipy in float64).  libvmaf's float_ssim is iqa's implementation of exactly that formula
+    for pictures with min(w, h) < 384 (no decimation); iqa's three-term l*c*s with C3 = C2/2 equals the two-term form."""
+    cv2 = pytest.importorskip("cv2")
+    from scipy.ndimage import correlate1d
+    w, h = 320, 180
+    for seed in (4, 11):
+        (ref, _, _), (dis, _, _) = synth.frame_pair(seed, 1, w, h, 8)
+        sse = oracle.sse(ref, dis, 8)
+        assert oracle.psnr_from_sse(sse, 8, w, h) == pytest.approx(cv2.PSNR(ref, dis), abs=1e-9)
+        k = np.exp(-0.5 * (np.arange(-5, 6) / 1.5) ** 2)
+        k /= k.sum()
+
+        def g(a):
+            return correlate1d(correlate1d(a, k, axis=0, mode="constant"), k, axis=1, mode="constant")[5:-5, 5:-5]
+
+        x, y = ref.astype(np.float64), dis.astype(np.float64)
+        mx, my = g(x), g(y)
+        sxx, syy, sxy = g(x * x) - mx * mx, g(y * y) - my * my, g(x * y) - mx * my
+        c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+        ssim = float(np.mean((2 * mx * my + c1) * (2 * sxy + c2) / ((mx * mx + my * my + c1) * (sxx + syy + c2))))
+        got = oracle.float_features(ref, dis, 8, ssim=True)["float_ssim"]
+        # iqa works in float32 (sums of x^2 up to 65025 before the variance subtraction), so agreement with the float64
+        # textbook value is ~2e-4, two orders below what a wrong window, constant or region would cause
+        assert got == pytest.approx(ssim, abs=5e-4)
