@@ -60,6 +60,14 @@ template <int SCALE> struct AdmShifts {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// libvmaf's div_lookup[d] = 2^30 / d (truncated) for d in [1, 32768], computed instead of loaded at scales 1-3: there the
+// index is a normalised 15-bit value, the 256 KB table does not stay in L1 and each lookup was a dependent L2 round trip
+// (long_scoreboard was the top stall), while the
+// FP64 pipe is idle in this kernel.  Exact: 1/d is correctly rounded (error < 2^-53 relative), scaling by 2^30 is exact,
+// and for d not a power of two 2^30/d is at least 2^-15 away from an integer, so truncation cannot cross one
+// (tests/test_cpu_boundary.py checks all 32768 values against the integer division).
+__device__ __forceinline__ int adm_recip_q30(int d) { return __double2int_rz(__dmul_rn(__drcp_rn((double)d), 1073741824.0)); }
+
 // Decouple + CSF of one band position.  o/t: reference / distorted (h, v, d).
 // Returns |csf-weighted restored| per band, the 3-band sums of csf_f (neighbour weight 1/30) and of
 // the centre weight (1/15).
@@ -83,6 +91,7 @@ __device__ __forceinline__ void adm_decouple_csf(const int (&o)[3], const int (&
         if (ob == 0) {
             k = 32768;
         } else if (SCALE == 0) {
+            // scale 0: band values are small and cluster around 0, the table lines stay in L1 (the computed form measured 2 % slower here)
             const int tmp = (int)(((long long)__ldg(a.div_lookup + ob + 32768) * tb + 16384) >> 15);
             k = clampi(tmp, 0, 32768);
         } else {
@@ -93,7 +102,7 @@ __device__ __forceinline__ void adm_decouple_csf(const int (&o)[3], const int (&
                 sh = 17 - __clz(ao);
                 msb = (ao + (1u << (sh - 1))) >> sh;
             }
-            long long prod = (long long)__ldg(a.div_lookup + msb + 32768) * tb;
+            long long prod = (long long)adm_recip_q30((int)msb) * tb;
             if (ob < 0) prod = -prod;
             const long long tmp = (prod + (1ll << (14 + sh))) >> (15 + sh);
             k = (int)(tmp < 0 ? 0 : (tmp > 32768 ? 32768 : tmp));

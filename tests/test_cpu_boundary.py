@@ -153,3 +153,11 @@ def test_result_csv_combined_csv_and_metadata(tmp_path):
     assert m["vmaf_score"] == 91.0 and m["json_result"] == "T_vmaf.json" and m["psnr_file"] == "T_psnr.txt"
     assert m["ssim_file"] is None and m["video_details"]["resolution"] == "1920x1080"
     assert m["analysis_settings"]["model"] == "vmaf_v0.6.1" and "os" in m["system_info"]
+
+
+def test_adm_reciprocal_formula_is_exact():
+    """The ADM kernels compute libvmaf's div_lookup entries (2^30 / d, truncated) as trunc(RN(1/d) * 2^30) in double
+    instead of loading a 256 KB table; IEEE double arithmetic in numpy is the same arithmetic: all 32768 divisors."""
+    import numpy as np
+    d = np.arange(1, 32769, dtype=np.int64)
+    assert np.array_equal(np.trunc((1.0 / d.astype(np.float64)) * 1073741824.0).astype(np.int64), 1073741824 // d)
