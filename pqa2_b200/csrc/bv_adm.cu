@@ -153,7 +153,7 @@ template <> struct StageStore<int32_t> {
 
 // Persistent CTAs over (frame, tile) work items with register prefetch of the next tile's samples.
 template <int SCALE, typename TIn>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(AT_THREADS, SCALE == 0 ? 3 : 2)
 adm_scale_kernel(BvBatch batch, AdmArgs a, BvDiv tiles_x, BvDiv tiles_per_frame, int total_tiles)
 {
     using Stage = typename AdmTypes<SCALE>::Stage;
@@ -483,7 +483,8 @@ void launch_scale(const BvBatch &b, const AdmArgs &a, cudaStream_t st)
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
-    const int ctas = total < 2 * sms ? total : 2 * sms;
+    const int per_sm = SCALE == 0 ? 3 : 2;
+    const int ctas = total < per_sm * sms ? total : per_sm * sms;
     adm_scale_kernel<SCALE, TIn><<<ctas, AT_THREADS, smem, st>>>(b, a, bv_make_div(tiles_x, tiles_per_frame), bv_make_div(tiles_per_frame, total), total);
 }
 
