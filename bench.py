@@ -235,6 +235,29 @@ def reference_arm(args, wl, wname):
     return 0
 
 
+def bind_to_gpu_numa_node(local: int) -> str:
+    """One process per GPU: run on (and therefore first-touch the pinned frame buffers from) the CPUs of the NUMA node the
+    GPU hangs off, so that the H2D stream of rank r does not cross the socket interconnect.  Best effort; returns a note."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out                    # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa: rank bound to node {node} ({len(cpus)} cpus)"
+    except Exception as e:          # noqa: BLE001
+        return f"numa: not bound ({type(e).__name__})"
+    return "numa: not bound"
+
+
 def wl_dtype(wl) -> str:
     return "f32" if "float" in wl["model"] else "int32/int64 fixed-point"
 
@@ -293,6 +316,7 @@ def main() -> int:
             wl = WORKLOADS[wname]
 
     dist = None
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -452,6 +476,8 @@ def main() -> int:
                "timer": "host wall clock around K engine.analyze calls (pinned host frames -> H2D, kernels, feature D2H, "
                         "SVR, pooling), max over ranks",
                "pooled_vmaf_mean": res["pooled_metrics"]["vmaf"]["mean"]}
+        if numa_note:
+            e2e["host_placement"] = numa_note
 
     if rank != 0:
         if dist is not None:
