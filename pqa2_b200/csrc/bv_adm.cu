@@ -469,12 +469,8 @@ adm_rows_finish_kernel(BvBatch batch, AdmFinishArgs a)
 template <int SCALE, typename TIn>
 void launch_scale(const BvBatch &b, const AdmArgs &a, cudaStream_t st)
 {
-    static bool configured = false;
     const size_t smem = adm_smem<SCALE>();
-    if (!configured) {
-        cudaFuncSetAttribute(adm_scale_kernel<SCALE, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    bv_allow_smem<&adm_scale_kernel<SCALE, TIn>>(smem);
     const int tiles_x = (a.sp.w + AT_W - 1) / AT_W, tiles_per_frame = tiles_x * ((a.sp.h + AT_H - 1) / AT_H);
     const int total = tiles_per_frame * b.n;
     static int sms = 0;

@@ -1,5 +1,6 @@
 // Shared device helpers and the internal kernel-launch interface of libb200vmaf (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -28,6 +29,22 @@ __device__ __forceinline__ int bv_sym(int i, int n)
     if (i < 0) return -1 - i;
     if (i >= n) return 2 * n - i - 1;
     return i;
+}
+
+// ---- opt-in to > 48 KB of dynamic shared memory -------------------------------------------------
+// cudaFuncSetAttribute applies to the CURRENT device only, and one process may drive several GPUs (one context and one
+// host thread per device): remember the opt-in per (kernel instantiation, device), not per process.
+template <auto Kernel>
+inline void bv_allow_smem(size_t bytes)
+{
+    static std::atomic<unsigned long long> done{ 0ull };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+        cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        done.fetch_or(bit, std::memory_order_release);
+    }
 }
 
 // ---- division by a launch-invariant divisor -------------------------------------------------

@@ -411,3 +411,21 @@ def test_repeated_runs_are_bit_identical():
             runs.append([(tuple(r.raw[:]), tuple(r.f_vif_scale[:]), r.f_adm2, r.f_motion, r.float_ssim, r.float_ms_ssim)
                          for r in out])
     assert runs[0] == runs[1] == runs[2] == runs[3]
+
+
+def test_two_gpus_in_one_process_match_one_gpu():
+    """VMAFAnalyzer's default is every GPU of the box from ONE process (one context + host thread per device).  Function
+    attributes (the > 48 KB dynamic shared memory opt-in) and constant uploads are per device: a second device must get
+    its own.  Needs 2 GPUs; skipped on single-GPU boxes."""
+    from pqa2_b200 import engine, model as M
+    if L.load().bv_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    src = engine.SynthSource(640, 360, 8, 12, seed=5, chroma=0)
+    for name in ("vmaf_v0.6.1", "vmaf_float_v0.6.1"):
+        mdl = M.resolve_model(name)
+        opt1 = engine.EngineOptions(psnr=True, ssim=True, ms_ssim=True, devices=(0,))
+        opt2 = engine.EngineOptions(psnr=True, ssim=True, ms_ssim=True, devices=(0, 1))
+        opt3 = engine.EngineOptions(psnr=True, ssim=True, ms_ssim=True, devices=(1,))
+        one, two, other = (engine.analyze(src, mdl, o) for o in (opt1, opt2, opt3))
+        assert [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in two["frames"]]
+        assert [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in other["frames"]]
