@@ -64,7 +64,8 @@ def kernel_bytes(name: str, w: int, h: int, bps: int) -> float | None:
         "psnr_sse_y": 2 * px * bps,
         # float extractors: fp32 pyramids / bands / blur
         "f_motion_blur": px * bps + px * 4, "f_motion_sad": px * 4,
-        "f_vif_stat_s0": 2 * px * bps, "f_vif_subsample_s1": 2 * px * bps + 2 * lv[1] * 4,
+        # f_vif_subsample_s1 also writes the motion feature's blurred reference (fused staging)
+        "f_vif_stat_s0": 2 * px * bps, "f_vif_subsample_s1": 2 * px * bps + 2 * lv[1] * 4 + px * 4,
         "f_vif_stat_s1": 2 * lv[1] * 4, "f_vif_subsample_s2": 2 * lv[1] * 4 + 2 * lv[2] * 4,
         "f_vif_stat_s2": 2 * lv[2] * 4, "f_vif_subsample_s3": 2 * lv[2] * 4 + 2 * lv[3] * 4,
         "f_vif_stat_s3": 2 * lv[3] * 4,

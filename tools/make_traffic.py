@@ -11,7 +11,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORDER = {
-    "1080p-float": ["psnr_sse_y", "f_motion_blur", "f_motion_sad", "f_vif_stat_s0", "f_vif_subsample_s1", "f_vif_stat_s1",
+    # the motion blur rides in f_vif_subsample_s1 (fused staging); its SAD follows that kernel
+    "1080p-float": ["psnr_sse_y", "f_vif_stat_s0", "f_vif_subsample_s1", "f_motion_sad", "f_vif_stat_s1",
                     "f_vif_subsample_s2", "f_vif_stat_s2", "f_vif_subsample_s3", "f_vif_stat_s3", "f_adm_scale0",
                     "f_adm_scale1", "f_adm_scale2", "f_adm_scale3", "ssim_decimate", "ssim_maps", "ms_ssim_maps_s0",
                     "ms_ssim_lpf_s1", "ms_ssim_maps_s1", "ms_ssim_lpf_s2", "ms_ssim_maps_s2", "ms_ssim_lpf_s3",

@@ -11,7 +11,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_r01_reference_1
 # ncu passes: only after the plain runs above exited; numbers printed under ncu are never bench values
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_r01_$TAG.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_launches_$TAG.log 2>&1
-ncu --set full --clock-control none --launch-skip 520 -c 26 -f -o $O/full_float_$TAG \
+ncu --set full --clock-control none --launch-skip 500 -c 25 -f -o $O/full_float_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_full_float_$TAG.log 2>&1
 ncu -i $O/full_float_$TAG.ncu-rep --page raw --csv > $O/raw_float_$TAG.csv
 ncu --set full --clock-control none --launch-skip 280 -c 14 -f -o $O/full_int_$TAG \
