@@ -1,0 +1,150 @@
+"""Host side of the engine without a GPU: `engine.analyze` drives a stand-in for the CUDA context (same methods as
+`extractor.FeatureExtractor`) and the test checks what the host loop is responsible for -- frame flags (first frame,
+lead-in, n_subsample), launch-group kicks, shard ranges with lead-in frames, the motion2 rule over shard borders, the SVR
+(host libsvm path of the C library), pooling -- against a single-shard run and against direct arithmetic.
+Reference behaviour restated: libvmaf frame flow as reached from app/vmaf_analyzer.py:417."""
+import numpy as np
+import pytest
+
+from pqa2_b200 import _lib as L
+from pqa2_b200 import engine, model as M, report
+
+
+class FakeExtractor:
+    """Features are functions of the frame's content (here: of its first pixel = the global frame index)."""
+    instances = []
+
+    def __init__(self, width, height, bpc, chroma, features, device=0, **kw):
+        self.batch = kw.get("batch_frames") or 32
+        self.frames, self.kicks, self.kw = [], [], kw
+        FakeExtractor.instances.append(self)
+
+    batch_frames = property(lambda self: self.batch)
+    kernel_launches = 0
+
+    def submit(self, frame_index, ref_planes, dis_planes, flags=0):
+        self.frames.append((int(frame_index), int(ref_planes[0][0, 0]), int(flags)))
+
+    def kick(self):
+        self.kicks.append(len(self.frames))
+
+    def wait_uploads(self):
+        pass
+
+    def flush(self):
+        pass
+
+    def reset(self):
+        self.frames.clear()
+
+    def cancel(self):
+        pass
+
+    def close(self):
+        pass
+
+    def fetch(self, first=0, count=None):
+        arr = (L.BvFrameFeatures * len(self.frames))()
+        prev = None
+        for k, (idx, content, flags) in enumerate(self.frames):
+            f = arr[k]
+            f.frame_index, f.flags = idx, flags
+            lead = bool(flags & L.FRAME_LEAD_IN)
+            spatial = not (flags & (L.FRAME_LEAD_IN | L.FRAME_SKIP_SPATIAL))
+            valid = 0
+            if not lead:
+                f.motion = 0.0 if (flags & L.FRAME_FIRST) or prev is None else abs(np.sin(content * 1.7) - np.sin(prev * 1.7)) * 5
+                valid |= L.FEAT_MOTION
+            if spatial:
+                for s in range(4):
+                    f.vif_scale[s] = 0.5 + 0.4 * np.cos(content * 0.3 + s) ** 2
+                    f.adm_scale[s] = 0.9
+                f.adm2 = 0.8 + 0.1 * np.sin(content) ** 2
+                f.psnr_y = 30.0 + content % 7
+                valid |= L.FEAT_VIF | L.FEAT_ADM | L.FEAT_PSNR_Y
+            f.valid_mask = valid
+            prev = content
+        return arr
+
+
+class Clip(engine.FrameSource):
+    width, height, bpc, chroma, fps = 64, 48, 8, 0, 30.0
+
+    def __init__(self, n):
+        self.nb_frames = n
+
+    def read_into(self, i, ref_planes, dis_planes, luma_only):
+        ref_planes[0][...] = i % 251
+        dis_planes[0][...] = (i * 3) % 251
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    FakeExtractor.instances = []
+    monkeypatch.setattr(engine, "FeatureExtractor", FakeExtractor)
+    monkeypatch.setattr(engine, "pinned_empty", lambda shape, dtype: np.empty(shape, dtype))
+    return FakeExtractor
+
+
+def _opt(**kw):
+    return engine.EngineOptions(svr_on_device=False, **kw)
+
+
+def test_flags_kicks_and_shards(fake):
+    model = M.resolve_model("vmaf_v0.6.1")
+    n = 75
+    one = engine.analyze(Clip(n), model, _opt(psnr=True, devices=(0,)))
+    (fx,) = fake.instances
+    assert [i for i, _, _ in fx.frames] == list(range(n))
+    assert fx.frames[0][2] & L.FRAME_FIRST and not any(fl & L.FRAME_FIRST for _, _, fl in fx.frames[1:])
+    assert not any(fl & (L.FRAME_LEAD_IN | L.FRAME_SKIP_SPATIAL) for _, _, fl in fx.frames)
+    assert fx.kicks == [8]                                   # a short first group; no tail split at <= 1440p (32-frame groups)
+
+    fake.instances.clear()
+    three = engine.analyze(Clip(n), model, _opt(psnr=True, devices=(0, 0, 0)))
+    assert len(fake.instances) == 3
+    starts = sorted(fx.frames[0][0] for fx in fake.instances)
+    assert starts == [0, 24, 49]                              # shard 0 from frame 0; the others begin with their lead-in frame
+    for fx in fake.instances:
+        first_idx, _, fl0 = fx.frames[0]
+        assert fl0 & L.FRAME_FIRST
+        assert bool(fl0 & L.FRAME_LEAD_IN) == (first_idx != 0)
+        assert not any(fl & L.FRAME_LEAD_IN for _, _, fl in fx.frames[1:])
+    assert [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in three["frames"]]
+    assert one["pooled_metrics"] == three["pooled_metrics"] == report.pooled_metrics(one["frames"])
+
+    # motion2[i] = min(motion[i], motion[i+1]), last frame keeps its own; motion[0] = 0
+    m = [fr["metrics"]["integer_motion"] for fr in one["frames"]]
+    m2 = [fr["metrics"]["integer_motion2"] for fr in one["frames"]]
+    assert m[0] == 0.0 and m2 == [min(m[i], m[i + 1]) if i + 1 < n else m[i] for i in range(n)]
+    # the score is the C library's host SVR on (adm2, motion2, vif0..3) in the model's order
+    fr = one["frames"][10]["metrics"]
+    x = np.array([[fr["integer_adm2"], fr["integer_motion2"]] + [fr[f"integer_vif_scale{s}"] for s in range(4)]])
+    assert model.main.predict(x)[0] == fr["vmaf"]
+
+
+def test_n_subsample_scores_every_nth_frame_but_motion_sees_all(fake):
+    model = M.resolve_model("vmaf_v0.6.1")
+    res = engine.analyze(Clip(20), model, _opt(n_subsample=4))
+    (fx,) = fake.instances
+    assert [bool(fl & L.FRAME_SKIP_SPATIAL) for _, _, fl in fx.frames] == [i % 4 != 0 for i in range(20)]
+    assert [fr["frameNum"] for fr in res["frames"]] == [0, 4, 8, 12, 16]
+    assert all("integer_motion2" in fr["metrics"] and "vmaf" in fr["metrics"] for fr in res["frames"])
+
+
+def test_tail_split_only_for_reduced_group_sizes(fake, monkeypatch):
+    model = M.resolve_model("vmaf_v0.6.1")
+    engine.analyze(Clip(100), model, _opt(batch_frames=16))
+    (fx,) = fake.instances
+    # first kick after 8 frames, then when 8 and 4 frames are left (2160p-style 16-frame groups)
+    assert fx.kicks == [8, 92, 96]
+
+
+def test_frame_range_and_empty_clip(fake):
+    model = M.resolve_model("vmaf_v0.6.1")
+    res = engine.analyze(Clip(40), model, _opt(), frame_range=(10, 25))
+    assert [fr["frameNum"] for fr in res["frames"]] == list(range(10, 25))
+    (fx,) = fake.instances
+    assert fx.frames[0][0] == 9 and fx.frames[0][2] & L.FRAME_LEAD_IN          # frame 9 only feeds the motion state
+    with pytest.raises(ValueError):
+        engine.analyze(Clip(0), model, _opt())
