@@ -123,3 +123,21 @@ def test_oracle_psnr_and_ssim_against_independent_implementations():
         # iqa works in float32 (sums of x^2 up to 65025 before the variance subtraction), so agreement with the float64
         # textbook value is ~2e-4, two orders below what a wrong window, constant or region would cause
         assert got == pytest.approx(ssim, abs=5e-4)
+
+
+def test_synthetic_frames_exercise_every_branch():
+    """SURVEY.md §8d asks the synthetic clips to reach the VIF non-log branch (flat regions), the log branch, a gain above
+    1 (where the NEG limits bite) and the ADM angle flag both ways; a generator that stopped doing so would quietly
+    weaken every parity test built on it."""
+    w, h = 352, 288
+    (ref, _, _), (dis, _, _) = synth.frame_pair(3, 2, w, h, 8)
+    v = oracle.vif(ref, dis, 8)
+    acc = np.asarray(v["acc"])
+    assert acc[0, 3] > 0 and acc[0, 6] > 0, "scale 0 must see both the non-log and the log branch"
+    assert acc[0, 6] + acc[0, 3] == w * h                                  # every pixel takes exactly one of them
+    vneg = oracle.vif(ref, dis, 8, 1.0)
+    assert np.asarray(vneg["acc"])[0, 0] < acc[0, 0], "a gain limit of 1 must lower the numerator (sharpened patch)"
+    a, aneg = oracle.adm(ref, dis, 8), oracle.adm(ref, dis, 8, 1.0)
+    assert aneg["adm2"] < a["adm2"], "the ADM gain limit only acts where the angle flag is set"
+    same = oracle.adm(ref, ref, 8, 1.0)
+    assert abs(same["adm2"] - 1.0) < 1e-4
