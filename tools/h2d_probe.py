@@ -1,6 +1,6 @@
 """H2D bandwidth from pinned host memory as a function of chunk size and of the CPU/NUMA node the pinned buffer was
 allocated (first-touched) from.  Tool only (uses torch for brevity); informs the 4K e2e number, which is PCIe-bound."""
-import os, sys, time
+import os, time
 import torch
 
 def cpus_by_node():

@@ -1,5 +1,5 @@
 """Summarise an ncu launch list (`--metrics gpu__time_duration.sum --csv`): per kernel launches, mean time, share."""
-import csv, sys, collections, re
+import csv, sys, collections
 path, title = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
 rows = [r for r in csv.reader(open(path)) if r]
 hi = next(i for i, r in enumerate(rows) if r[0] == "ID")

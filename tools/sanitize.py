@@ -1,7 +1,6 @@
 """Small invocation of every kernel for compute-sanitizer (memcheck / racecheck): integer + float extractors, psnr, ffssim,
 bookend scan, two launch groups with a lead-in frame.  Usage: compute-sanitizer --tool racecheck python tools/sanitize.py"""
 import sys
-import numpy as np
 sys.path.insert(0, '.')
 from pqa2_b200 import _lib as L, synth, bookend
 from pqa2_b200.extractor import FeatureExtractor
