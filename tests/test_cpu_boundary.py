@@ -161,3 +161,28 @@ def test_adm_reciprocal_formula_is_exact():
     import numpy as np
     d = np.arange(1, 32769, dtype=np.int64)
     assert np.array_equal(np.trunc((1.0 / d.astype(np.float64)) * 1073741824.0).astype(np.int64), 1073741824 // d)
+
+
+def test_ffmpeg_stats_file_formats(tmp_path):
+    """Row a9: the files the reference's `psnr` / `ssim` ffmpeg passes leave behind (app/vmaf_analyzer.py:1027-1034,
+    :1057-1064) -- one line per frame, n from 1, FFmpeg's field names and precisions."""
+    import math
+    from pqa2_b200 import report
+    areas = [1920 * 1080, 960 * 540, 960 * 540]
+    p = tmp_path / "psnr.txt"
+    out = report.write_ffmpeg_psnr_stats(str(p), [{"mse": [4.0, 1.0, 0.25], "areas": areas},
+                                                    {"mse": [0.0, 0.0, 0.0], "areas": areas}], 8)
+    l1, l2 = p.read_text().splitlines()
+    avg = (4.0 * 4 + 1.0 + 0.25) / 6
+    db = lambda m: 10 * math.log10(255 * 255 / m)                     # noqa: E731
+    assert l1.split() == (f"n:1 mse_avg:{avg:.2f} mse_y:4.00 mse_u:1.00 mse_v:0.25 psnr_avg:{db(avg):.2f} "
+                          f"psnr_y:{db(4.0):.2f} psnr_u:{db(1.0):.2f} psnr_v:{db(0.25):.2f}").split()
+    assert l2.split()[:2] == ["n:2", "mse_avg:0.00"] and "psnr_avg:inf" in l2 and "psnr_y:inf" in l2
+    assert out["mse_avg"] == pytest.approx(avg / 2)
+    s = tmp_path / "ssim.txt"
+    report.write_ffmpeg_ssim_stats(str(s), [{"ssim": [0.9, 0.96, 0.98], "weights": areas},
+                                            {"ssim": [1.0, 1.0, 1.0], "weights": areas}])
+    a1, a2 = s.read_text().splitlines()
+    allv = (4 * 0.9 + 0.96 + 0.98) / 6                                # area-weighted = (4Y + U + V) / 6 at 4:2:0
+    assert a1 == "n:1 Y:%f U:%f V:%f All:%f (%f)" % (0.9, 0.96, 0.98, allv, -10 * math.log10(1 - allv))
+    assert a2 == "n:2 Y:1.000000 U:1.000000 V:1.000000 All:1.000000 (inf)"
