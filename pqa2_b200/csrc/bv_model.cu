@@ -5,6 +5,7 @@
 #include "bv_common.cuh"
 #include "../../include/b200vmaf.h"
 #include <math.h>
+#include <mutex>
 #include <vector>
 
 struct bv_model {
@@ -15,9 +16,15 @@ struct bv_model {
     int has_clip = 0;
     double tp[3] = { 0, 0, 0 };
     unsigned tflags = 0;
-    // device mirror (lazy, per device)
-    int dev = -1;
-    double *d_sv = nullptr, *d_coef = nullptr, *d_slopes = nullptr, *d_intercepts = nullptr;
+    // Device mirrors: one per GPU, created on first use under `mu` and never freed before bv_model_free, so
+    // a VmafModel shared by one worker thread per GPU (engine.analyze_batch, sweep.run_sweep) is safe: a thread on
+    // device A never sees (or frees) the buffers of device B.
+    struct Mirror {
+        int dev = -1;
+        double *d_sv = nullptr, *d_coef = nullptr, *d_slopes = nullptr, *d_intercepts = nullptr;
+    };
+    std::mutex mu;
+    std::vector<Mirror> mirrors;
 };
 
 namespace {
@@ -68,9 +75,9 @@ bv_model *bv_model_create(int n_feat, int n_sv, const double *sv, const double *
 void bv_model_free(bv_model *m)
 {
     if (!m) return;
-    if (m->dev >= 0) {
-        cudaSetDevice(m->dev);
-        cudaFree(m->d_sv); cudaFree(m->d_coef); cudaFree(m->d_slopes); cudaFree(m->d_intercepts);
+    for (const bv_model::Mirror &r : m->mirrors) {
+        if (cudaSetDevice(r.dev) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaFree(r.d_sv); cudaFree(r.d_coef); cudaFree(r.d_slopes); cudaFree(r.d_intercepts);
     }
     delete m;
 }
@@ -103,24 +110,35 @@ int bv_predict_device(const bv_model *cm, int device, const double *feat, int64_
     if (!m || !feat || !out || n < 0) return BV_ERR_ARG;
     if (n == 0) return 0;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return BV_ERR_CUDA; }
-    if (m->dev != device) {
-        if (m->dev >= 0) { cudaFree(m->d_sv); cudaFree(m->d_coef); cudaFree(m->d_slopes); cudaFree(m->d_intercepts); }
-        const size_t nsv = m->sv.size() * sizeof(double);
-        if (cudaMalloc(&m->d_sv, nsv) || cudaMalloc(&m->d_coef, m->coef.size() * sizeof(double)) ||
-            cudaMalloc(&m->d_slopes, m->slopes.size() * sizeof(double)) ||
-            cudaMalloc(&m->d_intercepts, m->intercepts.size() * sizeof(double))) { cudaGetLastError(); return BV_ERR_CUDA; }
-        cudaMemcpy(m->d_sv, m->sv.data(), nsv, cudaMemcpyHostToDevice);
-        cudaMemcpy(m->d_coef, m->coef.data(), m->coef.size() * sizeof(double), cudaMemcpyHostToDevice);
-        cudaMemcpy(m->d_slopes, m->slopes.data(), m->slopes.size() * sizeof(double), cudaMemcpyHostToDevice);
-        cudaMemcpy(m->d_intercepts, m->intercepts.data(), m->intercepts.size() * sizeof(double), cudaMemcpyHostToDevice);
-        m->dev = device;
+    bv_model::Mirror mir;
+    {
+        std::lock_guard<std::mutex> lock(m->mu);
+        for (const bv_model::Mirror &r : m->mirrors) if (r.dev == device) mir = r;
+        if (mir.dev < 0) {
+            bv_model::Mirror r;
+            const size_t nsv = m->sv.size() * sizeof(double), ncoef = m->coef.size() * sizeof(double),
+                         nsl = m->slopes.size() * sizeof(double);
+            if (cudaMalloc(&r.d_sv, nsv) || cudaMalloc(&r.d_coef, ncoef) || cudaMalloc(&r.d_slopes, nsl) ||
+                cudaMalloc(&r.d_intercepts, nsl) ||
+                cudaMemcpy(r.d_sv, m->sv.data(), nsv, cudaMemcpyHostToDevice) ||
+                cudaMemcpy(r.d_coef, m->coef.data(), ncoef, cudaMemcpyHostToDevice) ||
+                cudaMemcpy(r.d_slopes, m->slopes.data(), nsl, cudaMemcpyHostToDevice) ||
+                cudaMemcpy(r.d_intercepts, m->intercepts.data(), nsl, cudaMemcpyHostToDevice)) {
+                cudaGetLastError();
+                cudaFree(r.d_sv); cudaFree(r.d_coef); cudaFree(r.d_slopes); cudaFree(r.d_intercepts);
+                return BV_ERR_CUDA;
+            }
+            r.dev = device;
+            m->mirrors.push_back(r);
+            mir = r;
+        }
     }
     double *d_feat = nullptr, *d_out = nullptr;
     if (cudaMalloc(&d_feat, sizeof(double) * n * m->n_feat) || cudaMalloc(&d_out, sizeof(double) * n)) {
         cudaGetLastError(); cudaFree(d_feat); return BV_ERR_CUDA;
     }
     cudaMemcpy(d_feat, feat, sizeof(double) * n * m->n_feat, cudaMemcpyHostToDevice);
-    bv_launch_svr(d_feat, m->n_feat, m->d_slopes, m->d_intercepts, m->d_sv, m->d_coef, m->n_sv, m->gamma, m->rho,
+    bv_launch_svr(d_feat, m->n_feat, mir.d_slopes, mir.d_intercepts, mir.d_sv, mir.d_coef, m->n_sv, m->gamma, m->rho,
                   d_out, n, 0);
     cudaError_t e = cudaMemcpy(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost);
     cudaFree(d_feat); cudaFree(d_out);

@@ -21,6 +21,7 @@ from . import _lib as L
 from . import report
 from .extractor import FeatureExtractor, pinned_empty
 from .model import VmafModel
+from .yuvio import EndOfClip
 
 
 @dataclass
@@ -38,6 +39,8 @@ class EngineOptions:
     batch_frames: int = 0
     svr_on_device: bool = True
     extra_features: int = 0          # extra _lib.FEAT_* bits
+    float_motion: bool = False       # `feature=name=motion` (app/vmaf_analyzer.py:388-402): libvmaf's float motion
+                                     # extractor next to the model's own features -> `motion`, `motion2` in the log
 
 
 class FrameSource:
@@ -112,7 +115,7 @@ def _plane_shapes(src: FrameSource):
 def feature_mask(model: VmafModel, opt: EngineOptions) -> int:
     m = L.FEAT_VMAF_FLOAT if model.is_float else L.FEAT_VMAF_INT
     if opt.psnr:
-        m |= L.FEAT_PSNR_Y
+        m |= L.FEAT_PSNR_Y | L.FEAT_PSNR_UV      # psnr_y, psnr_cb, psnr_cr (chroma bits are inert for luma-only sources)
     if opt.ssim:
         m |= L.FEAT_FLOAT_SSIM
     if opt.ms_ssim:
@@ -121,6 +124,8 @@ def feature_mask(model: VmafModel, opt: EngineOptions) -> int:
         m |= L.FEAT_PSNR_Y | L.FEAT_PSNR_UV
     if opt.ffmpeg_ssim:
         m |= L.FEAT_FFSSIM
+    if opt.float_motion:
+        m |= L.FEAT_FLOAT_MOTION
     return m | opt.extra_features
 
 
@@ -139,7 +144,7 @@ class _Cancelled(Exception):
 
 def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: int, start: int, end: int,
                mask: int, rows: list, progress, cancel: threading.Event, errors: list, ctx_holder: list,
-               session: "Engine | None" = None):
+               session: "Engine | None" = None, shard: int = 0, lead_in: bool | None = None):
     handle = None
     fx = None
     try:
@@ -147,7 +152,9 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
         luma_only = not (mask & (L.FEAT_PSNR_UV | L.FEAT_FFSSIM)) or src.chroma in (0, 400)
         shapes = _plane_shapes(src)[: 1 if luma_only else 3]
         dtype = np.uint8 if src.bpc == 8 else np.uint16
-        key = (device, src.width, src.height, src.bpc, src.chroma if not luma_only else 0, mask,
+        # one context (and one pinned ring) per shard: two shards on the same GPU must never share a bv_ctx
+        # (include/b200vmaf.h: one host thread per ctx)
+        key = (device, shard, src.width, src.height, src.bpc, src.chroma if not luma_only else 0, mask,
                model.vif_enhn_gain_limit, model.adm_enhn_gain_limit, opt.batch_frames)
         fx = session._extractor(key) if session is not None else None
         if fx is None:
@@ -165,7 +172,7 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
         if not zero_copy:
             ring = session._ring(key, shapes, dtype, 2 * B) if session is not None else \
                 [([pinned_empty(s, dtype) for s in shapes], [pinned_empty(s, dtype) for s in shapes]) for _ in range(2 * B)]
-        lead = 1 if start > 0 else 0
+        lead = (1 if start > 0 else 0) if lead_in is None else (1 if lead_in and start > 0 else 0)
         ordinal = 0
         # pictures large enough for a reduced group size are upload-bound over PCIe: only there does a short last
         # launch shorten the call; at <= 1440p the GPU is the bottleneck and short groups would only run less efficiently
@@ -180,7 +187,13 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
                 if ordinal and ordinal % B == 0:
                     fx.wait_uploads()       # the half of the ring we are about to overwrite is free again
                 rp, dp = ring[ordinal % len(ring)]
-                handle.read_into(i, rp, dp, luma_only)
+                try:
+                    handle.read_into(i, rp, dp, luma_only)
+                except EndOfClip:
+                    # the container promised more frames than it decodes to (its frame count is an estimate): the
+                    # clip ends here, as it does for ffmpeg + libvmaf, which stop at the shorter input
+                    errors.append(("truncated", i))
+                    break
             flags = 0
             if i < start:
                 flags |= L.FRAME_LEAD_IN
@@ -209,6 +222,7 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
         errors.append(("cancelled", None))
     except Exception as e:            # surfaced by analyze(): the caller decides how to report
         errors.append(("error", e))
+        cancel.set()                  # a failed shard stops its siblings instead of letting them run to the end
     finally:
         if fx is not None and session is None:
             fx.close()
@@ -317,18 +331,6 @@ class Rows:
         self.present[frame_indices] = True
 
 
-def _copy_features(f) -> dict:
-    """Legacy dict form of one bv_frame_features record (kept for callers that build rows by hand)."""
-    return {
-        "valid": int(f.valid_mask), "raw": list(f.raw),
-        "motion": f.motion, "vif": list(f.vif_scale), "adm2": f.adm2, "adm_scale": list(f.adm_scale),
-        "adm_num": list(f.adm_num), "adm_den": list(f.adm_den), "vif_num": list(f.vif_num), "vif_den": list(f.vif_den),
-        "psnr": [f.psnr_y, f.psnr_cb, f.psnr_cr], "ffssim": list(f.ffssim),
-        "f_motion": f.f_motion, "f_vif": list(f.f_vif_scale), "f_adm2": f.f_adm2, "f_adm_scale": list(f.f_adm_scale),
-        "float_ssim": f.float_ssim, "float_ms_ssim": f.float_ms_ssim,
-    }
-
-
 def _egl_suffix(v: float) -> str:
     return "" if v == 100.0 else "_egl_%g" % v
 
@@ -394,7 +396,18 @@ def _build_frames_block(rows: Rows, model: VmafModel, opt: EngineOptions, device
     cols += [(f"{pre}vif_scale{k}{vs}", vif[:, k]) for k in range(4)]
     opt_cols = []
     if opt.psnr or opt.ffmpeg_psnr:
+        # libvmaf's psnr extractor logs all three planes when the pictures have chroma (integer_psnr.c, enable_chroma)
         opt_cols.append(("psnr_y", a["psnr_y"], L.FEAT_PSNR_Y))
+        opt_cols.append(("psnr_cb", a["psnr_cb"], L.FEAT_PSNR_UV))
+        opt_cols.append(("psnr_cr", a["psnr_cr"], L.FEAT_PSNR_UV))
+    if opt.float_motion and not is_f:
+        fm = np.array(a["f_motion"], np.float64)
+        if n:
+            fm[0] = 0.0
+        fm2 = fm.copy()
+        if n > 1:
+            fm2[:-1] = np.minimum(fm[:-1], fm[1:])
+        cols += [("motion2", fm2), ("motion", fm)]
     opt_cols.append(("float_ssim", a["float_ssim"], L.FEAT_FLOAT_SSIM))
     opt_cols.append(("float_ms_ssim", a["float_ms_ssim"], L.FEAT_FLOAT_MS_SSIM))
     names = [c[0] for c in cols]
@@ -463,6 +476,8 @@ def build_frames(rows, model: VmafModel, opt: EngineOptions, device: int | None,
             m[f"{pre}vif_scale{s}{vs}"] = vif[s]
         if r["valid"] & L.FEAT_PSNR_Y and (opt.psnr or opt.ffmpeg_psnr):
             m["psnr_y"] = r["psnr"][0]
+            if r["valid"] & L.FEAT_PSNR_UV:
+                m["psnr_cb"], m["psnr_cr"] = r["psnr"][1], r["psnr"][2]
         if r["valid"] & L.FEAT_FLOAT_SSIM:
             m["float_ssim"] = r["float_ssim"]
         if r["valid"] & L.FEAT_FLOAT_MS_SSIM:
@@ -554,24 +569,29 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
     holders: list = []
     t0 = time.perf_counter()
     threads = []
-    for dev, (a, b) in zip(devices, ranges):
+    for k, (dev, (a, b)) in enumerate(zip(devices, ranges)):
         if b <= a:
             continue
+        # a frame_range is scored as libvmaf would score the trimmed clip: its first frame has no predecessor
+        # (motion = 0), so only the shards after the first one get a lead-in frame
         th = threading.Thread(target=_run_shard, args=(src, model, opt, dev, a, b, mask, rows, progress, cancel,
-                                                       errors, holders, session), daemon=True)
+                                                       errors, holders, session, k, a > first), daemon=True)
         th.start()
         threads.append(th)
     for th in threads:
         th.join()
-    if any(k == "cancelled" for k, _ in errors) or cancel.is_set():
-        return None
-    for k, e in errors:
+    for k, e in errors:               # an engine error wins over the cancellation it triggered in the sibling shards
         if k == "error":
             raise e
+    if any(k == "cancelled" for k, _ in errors) or cancel.is_set():
+        return None
+    cut = [e for k, e in errors if k == "truncated"]
+    if cut:
+        last = min(cut)
+        n = last - first
+        if n <= 0:
+            raise EOFError("no frame could be decoded")
     rows_used = rows[first:last]
-    if first > 0:
-        # a sub-range does not know the frame before it: libvmaf would have started at index 0 too
-        pass
     pooled_out: dict = {}
     frames = build_frames(rows_used, model, opt, devices[0], pooled_out)
     for fr in frames:

@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import threading
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -19,6 +20,7 @@ import numpy as np
 from . import _lib as L
 
 MODELS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
+_HANDLE_LOCK = threading.Lock()          # SvrModel.handle(): one bv_model per SvrModel even when worker threads race
 
 
 @dataclass
@@ -65,7 +67,11 @@ class SvrModel:
 
     # ---- C ABI -------------------------------------------------------------------------------
     def handle(self):
-        if self._handle is None:
+        if self._handle is not None:
+            return self._handle
+        with _HANDLE_LOCK:
+            if self._handle is not None:
+                return self._handle
             lib = L.load()
             pd = C.POINTER(C.c_double)
             sv = np.ascontiguousarray(self.sv, np.float64)

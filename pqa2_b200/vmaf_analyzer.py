@@ -145,7 +145,7 @@ class VMAFAnalyzer(QObject):
             info = yuvio.probe(video_path)
             fps = info.fps
             return {"path": video_path, "duration": (info.nb_frames / fps) if fps else 0.0, "frame_rate": fps,
-                    "width": info.width, "height": info.height, "pix_fmt": info.pix_fmt, "codec_name": "rawvideo",
+                    "width": info.width, "height": info.height, "pix_fmt": info.pix_fmt, "codec_name": info.codec_name,
                     "bit_rate": int(info.frame_bytes * 8 * fps), "nb_frames": info.nb_frames}
         except Exception as e:               # noqa: BLE001  (reference :233-240 returns None on any failure)
             logger.error(f"Error getting video metadata for {video_path}: {e}")
@@ -210,7 +210,14 @@ class VMAFAnalyzer(QObject):
         extra = self.pool_method != "mean"
         opt = engine.EngineOptions(n_subsample=max(1, int(self.feature_subsample)), psnr=extra, ssim=extra,
                                    ffmpeg_psnr=bool(self.psnr_enabled) and ref_info.chroma != 400,
-                                   ffmpeg_ssim=bool(self.ssim_enabled) and ref_info.chroma != 400, devices=devices)
+                                   ffmpeg_ssim=bool(self.ssim_enabled) and ref_info.chroma != 400, devices=devices,
+                                   # :388-402: every `feature=` item the reference appends ends in libvmaf's float
+                                   # `motion` extractor (the vif_scaleN / adm2 items name no extractor of their own
+                                   # and the last `feature=` wins), so both flags add `motion` / `motion2` to the log
+                                   float_motion=bool(self.enable_motion_score or self.enable_temporal_features))
+        if ref_info.decoder == "cv2" or dis_info.decoder == "cv2":
+            # container decode is sequential (seeking is not frame-exact): one shard, one decoder per file
+            opt.devices = devices[:1]
         src = engine.FileSource(ref_info, dis_info)
         last = [-1]
 

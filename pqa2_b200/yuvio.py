@@ -26,6 +26,7 @@ class ClipInfo:
     header_bytes: int = 0
     frame_header_bytes: int = 0
     decoder: str = "raw"          # "raw" (y4m / planar yuv) or "cv2" (container decoded by cv2's bundled libavcodec, luma only)
+    codec_name: str = "rawvideo"  # ffprobe's codec_name (app/vmaf_analyzer.py:221-231); containers report their stream's codec
 
     @property
     def fps(self) -> float:
@@ -137,15 +138,31 @@ def _probe_container(path: str) -> ClipInfo:
         w, h = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
         n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
         fps = float(cap.get(cv2.CAP_PROP_FPS)) or 30.0
+        cc = int(cap.get(cv2.CAP_PROP_FOURCC))
     finally:
         cap.release()
     if w <= 0 or h <= 0:
         raise ValueError(f"{path}: no video stream")
-    return ClipInfo(path, w, h, 8, 400, int(round(fps * 1000)), 1000, nb_frames=n, decoder="cv2")
+    tag = "".join(chr((cc >> (8 * k)) & 0xFF) for k in range(4)).strip("\0 ").lower()
+    return ClipInfo(path, w, h, 8, 400, int(round(fps * 1000)), 1000, nb_frames=n, decoder="cv2",
+                    codec_name=_FOURCC_CODEC.get(tag, tag or "unknown"))
+
+
+# container fourcc -> the codec_name ffprobe prints for it
+_FOURCC_CODEC = {"avc1": "h264", "h264": "h264", "x264": "h264", "hev1": "hevc", "hvc1": "hevc", "hevc": "hevc",
+                 "mp4v": "mpeg4", "fmp4": "mpeg4", "xvid": "mpeg4", "vp09": "vp9", "vp90": "vp9", "vp80": "vp8",
+                 "av01": "av1", "mjpg": "mjpeg", "apch": "prores", "apcn": "prores", "ffv1": "ffv1"}
+
+
+class EndOfClip(EOFError):
+    """The decoder ran out of frames before the container's (estimated) frame count: the clip ends here, as it would
+    for ffmpeg + libvmaf, which stop at the shorter input."""
 
 
 class _Cv2Reader:
-    """Luma planes of a container file, decoded by cv2 (sequential; seeks when asked for another frame)."""
+    """Luma planes of a container file, decoded by cv2.  Strictly sequential: CAP_PROP_POS_FRAMES is not frame-exact
+    for H.264 with B-frames / VFR streams, so a frame further ahead is reached by decoding and discarding, and a
+    frame behind the cursor by reopening the file -- never by seeking."""
 
     def __init__(self, info: ClipInfo):
         import cv2
@@ -154,8 +171,14 @@ class _Cv2Reader:
             cv2.utils.logging.setLogLevel(cv2.utils.logging.LOG_LEVEL_ERROR)
         except Exception:                                  # noqa: BLE001
             pass
-        self._cap = cv2.VideoCapture(info.path)
-        self._cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+        self._cap = None
+        self._open()
+
+    def _open(self):
+        if self._cap is not None:
+            self._cap.release()
+        self._cap = self._cv2.VideoCapture(self.info.path)
+        self._cap.set(self._cv2.CAP_PROP_CONVERT_RGB, 0)
         self._next = 0
 
     def close(self):
@@ -168,15 +191,23 @@ class _Cv2Reader:
         return [np.empty((self.info.height, self.info.width), np.uint8)]
 
     def read_into(self, i: int, planes, luma_only: bool = False) -> None:
-        if i != self._next:
-            self._cap.set(self._cv2.CAP_PROP_POS_FRAMES, i)
+        if i < self._next:
+            self._open()
+        while self._next < i:                               # decode and discard up to the requested frame
+            if not self._cap.grab():
+                raise EndOfClip(f"{self.info.path}: stream ends at frame {self._next}")
+            self._next += 1
         ok, fr = self._cap.read()
         if not ok or fr is None:
-            raise EOFError(f"{self.info.path}: cannot decode frame {i}")
+            if i == 0:
+                raise EOFError(f"{self.info.path}: cannot decode the first frame")
+            raise EndOfClip(f"{self.info.path}: stream ends at frame {i}")
         self._next = i + 1
         h, w = self.info.height, self.info.width
-        if fr.ndim == 3:                                    # backend ignored CONVERT_RGB=0: BGR -> BT.601 luma
-            fr = self._cv2.cvtColor(fr, self._cv2.COLOR_BGR2YUV)[:, :, 0]
+        if fr.ndim == 3:
+            # the backend ignored CONVERT_RGB=0 and converted to BGR: recomputing Y from it is a range / matrix round
+            # trip, not the decoder's luma, and would change scores silently
+            raise ValueError(f"{self.info.path}: this cv2 build does not hand back the decoder's luma plane")
         y = fr.reshape(-1, w)[:h]                           # (h, w) luma; some builds return the whole I420 buffer (3h/2, w)
         planes[0][...] = y
 

@@ -181,9 +181,15 @@ def test_container_decode_through_cv2(tmp_path):
         # limited-range luma of a lossy encode: 16 + 219/255 * gray, within a few code values on average
         want = 16.0 + lum[f].astype(np.float64) * (219.0 / 255.0)
         assert pl[0].shape == (h, w) and np.abs(pl[0] - want).mean() < 4.0
+    # past the decodable end: the clip ends there (ffmpeg + libvmaf stop at the shorter input), no seek involved
+    with pytest.raises(yuvio.EndOfClip):
+        r.read_into(n + 3, pl, True)
+    r.read_into(1, pl, True)                     # behind the cursor: reopened and decoded forward, never seeked
+    assert np.abs(pl[0] - (16.0 + lum[1].astype(np.float64) * (219.0 / 255.0))).mean() < 4.0
     r.close()
     meta = VMAFAnalyzer().get_video_metadata(path)
     assert meta["width"] == w and meta["nb_frames"] == n
+    assert meta["codec_name"] == "mpeg4"         # ffprobe's name of the stream's codec, not "rawvideo"
 
 
 def test_libvmaf_filter_string_round_trip():

@@ -16,6 +16,7 @@ class FakeExtractor:
 
     def __init__(self, width, height, bpc, chroma, features, device=0, **kw):
         self.batch = kw.get("batch_frames") or 32
+        self.chroma, self.features = chroma, features
         self.frames, self.kicks, self.kw = [], [], kw
         FakeExtractor.instances.append(self)
 
@@ -62,6 +63,12 @@ class FakeExtractor:
                 f.adm2 = 0.8 + 0.1 * np.sin(content) ** 2
                 f.psnr_y = 30.0 + content % 7
                 valid |= L.FEAT_VIF | L.FEAT_ADM | L.FEAT_PSNR_Y
+                if self.chroma not in (0, 400) and self.features & L.FEAT_PSNR_UV:
+                    f.psnr_cb, f.psnr_cr = 40.0 + content % 5, 41.0 + content % 3
+                    valid |= L.FEAT_PSNR_UV
+            if self.features & L.FEAT_FLOAT_MOTION and not lead:
+                f.f_motion = 0.0 if (flags & L.FRAME_FIRST) or prev is None else 1.0 + (content % 4)
+                valid |= L.FEAT_FLOAT_MOTION
             f.valid_mask = valid
             prev = content
         return arr
@@ -145,6 +152,52 @@ def test_frame_range_and_empty_clip(fake):
     res = engine.analyze(Clip(40), model, _opt(), frame_range=(10, 25))
     assert [fr["frameNum"] for fr in res["frames"]] == list(range(10, 25))
     (fx,) = fake.instances
-    assert fx.frames[0][0] == 9 and fx.frames[0][2] & L.FRAME_LEAD_IN          # frame 9 only feeds the motion state
+    # a frame range is scored like the trimmed clip: its first frame has no predecessor (libvmaf index 0: motion = 0)
+    assert fx.frames[0][0] == 10 and fx.frames[0][2] & L.FRAME_FIRST and not fx.frames[0][2] & L.FRAME_LEAD_IN
+    assert res["frames"][0]["metrics"]["integer_motion"] == 0.0
+    fake.instances.clear()
+    two = engine.analyze(Clip(40), model, _opt(devices=(0, 0)), frame_range=(10, 25))
+    assert [fr["metrics"] for fr in two["frames"]] == [fr["metrics"] for fr in res["frames"]]
+    assert sorted(fx.frames[0][0] for fx in fake.instances) == [10, 16]          # only the second shard gets a lead-in (frame 16)
     with pytest.raises(ValueError):
         engine.analyze(Clip(0), model, _opt())
+
+
+class ChromaClip(Clip):
+    chroma = 420
+
+    def read_into(self, i, ref_planes, dis_planes, luma_only):
+        for p in ref_planes:
+            p[...] = i % 251
+        for p in dis_planes:
+            p[...] = (i * 3) % 251
+
+
+def test_psnr_logs_all_three_planes_and_feature_motion_adds_the_float_extractor(fake):
+    """libvmaf `psnr=1` (app/vmaf_analyzer.py:385) logs psnr_y, psnr_cb, psnr_cr for pictures with chroma (the CSV export
+    of results_tab.py:3009-3026 takes its header from these keys); `feature=name=motion` (:388-402) adds the float
+    motion extractor's `motion` / `motion2` next to the integer model's features."""
+    model = M.resolve_model("vmaf_v0.6.1")
+    res = engine.analyze(ChromaClip(12), model, _opt(psnr=True, float_motion=True))
+    m = res["frames"][5]["metrics"]
+    assert {"psnr_y", "psnr_cb", "psnr_cr", "motion", "motion2", "integer_motion", "integer_motion2", "vmaf"} <= set(m)
+    fm = [fr["metrics"]["motion"] for fr in res["frames"]]
+    assert fm[0] == 0.0 and [fr["metrics"]["motion2"] for fr in res["frames"]] == \
+        [min(fm[i], fm[i + 1]) if i + 1 < 12 else fm[i] for i in range(12)]
+    assert set(res["pooled_metrics"]) >= {"psnr_cb", "psnr_cr", "motion2"}
+    # luma-only pictures: no chroma PSNR, as libvmaf for gray input
+    fake.instances.clear()
+    res = engine.analyze(Clip(4), model, _opt(psnr=True))
+    assert "psnr_y" in res["frames"][0]["metrics"] and "psnr_cb" not in res["frames"][0]["metrics"]
+
+
+def test_failed_shard_stops_its_siblings_and_the_error_surfaces(fake, monkeypatch):
+    class Boom(Clip):
+        def read_into(self, i, ref_planes, dis_planes, luma_only):
+            if i == 30:
+                raise OSError("disk gone")
+            super().read_into(i, ref_planes, dis_planes, luma_only)
+
+    with pytest.raises(OSError):
+        engine.analyze(Boom(4000), M.resolve_model("vmaf_v0.6.1"), _opt(devices=(0, 0)))
+    assert max(len(fx.frames) for fx in fake.instances) < 2000           # the healthy shard did not run to its end
