@@ -10,8 +10,17 @@ SURVEY.md §8e).  `value` = frame pairs per second over all GPUs with the clips 
 `e2e` = the same through the public engine call (pqa2_b200.engine.analyze) from pinned HOST frames,
 host->device copies and the feature read-back inside the timed region.
 
+Headline workload (identical at every N): configs[1].  Next to it, in the same JSON line:
+  workloads      (N = 1)  the integer v0.6.1 configurations BASELINE's metric names -- 1080p-int (configs[0] shape)
+                          and 4k-int (configs[2]) -- each with value / e2e / roofline / cpu_baseline
+  sharded_4k     (all N)  ONE 2160p 10-bit clip (configs[2]) split into contiguous frame chunks with a one-frame lead-in
+                          over the N ranks (pqa2_b200.dist.analyze_distributed), rows gathered on rank 0; at N > 1 rank 0
+                          re-scores the clip alone and the per-frame results must be bit-identical
+  batch          (all N)  configs[4]: 64 clips of 300 1080p frames dealt over the ranks, one pooled report per clip
+  file_e2e       (N = 1)  the drop-in call itself: VMAFAnalyzer.analyze_videos() on a 300-frame 1080p .y4m pair
+
 Workloads (BASELINE.json `configs`):
-  1080p-float  configs[1]: 1080p yuv420p 8-bit, vmaf_float_v0.6.1 + psnr + float_ssim + float_ms_ssim
+  1080p-float  configs[1]: 1080p yuv420p 8-bit, vmaf_float_v0.6.1 + psnr (y, cb, cr) + float_ssim + float_ms_ssim
   1080p-int    configs[0] shape: 1080p 8-bit, vmaf_v0.6.1 (integer extractors)
   4k-int       configs[2]: 2160p yuv420p10le, vmaf_4k_v0.6.1
 """
@@ -20,6 +29,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import shutil
 import statistics
 import subprocess
 import sys
@@ -37,13 +47,18 @@ WORKLOADS = {
     "1080p-int": dict(w=1920, h=1080, bpc=8, model="vmaf_v0.6.1", psnr=False, ssim=False, ms_ssim=False,
                       frames_per_step=512, pool=64, cfg="configs[0] shape"),
     "4k-int": dict(w=3840, h=2160, bpc=10, model="vmaf_4k_v0.6.1", psnr=False, ssim=False, ms_ssim=False,
-                   frames_per_step=256, pool=24, cfg="configs[2]"),
+                   frames_per_step=256, pool=16, cfg="configs[2]"),
 }
+SHARDED_FRAMES = 3600          # configs[2]: 2160p 60 fps, one minute
+BATCH_CLIPS, BATCH_FRAMES = 64, 300      # configs[4]
+FILE_FRAMES = 300              # configs[0]
+
 
 # Algorithmic bytes per frame pair of each kernel at (w, h, bytes per sample): unique bytes the
 # kernel must read + must write (DESIGN.md "Kernels").
 def kernel_bytes(name: str, w: int, h: int, bps: int) -> float | None:
     px = w * h
+    cpx = ((w + 1) // 2) * ((h + 1) // 2)
     lv = [((w >> s) * (h >> s)) for s in range(4)]                       # VIF level pixel counts
     ad = []
     cw, ch = w, h
@@ -61,7 +76,8 @@ def kernel_bytes(name: str, w: int, h: int, bps: int) -> float | None:
         "vif_stat_s3": 2 * lv[3] * 2,
         "adm_scale0": 2 * px * bps + 2 * ad[0] * 2, "adm_scale1": 2 * ad[0] * 2 + 2 * ad[1] * 4,
         "adm_scale2": 2 * ad[1] * 4 + 2 * ad[2] * 4, "adm_scale3": 2 * ad[2] * 4,
-        "psnr_sse_y": 2 * px * bps,
+        "psnr_sse_y": 2 * px * bps, "psnr_sse_u": 2 * cpx * bps, "psnr_sse_v": 2 * cpx * bps,
+        "ffssim_y": 2 * px * bps, "ffssim_u": 2 * cpx * bps, "ffssim_v": 2 * cpx * bps,
         # float extractors: fp32 pyramids / bands / blur
         "f_motion_blur": px * bps + px * 4, "f_motion_sad": px * 4,
         # f_vif_subsample_s1 also writes the motion feature's blurred reference (fused staging)
@@ -78,7 +94,7 @@ def kernel_bytes(name: str, w: int, h: int, bps: int) -> float | None:
     t["ssim_decimate"] = 2 * px * bps + 2 * sp * 4
     t["ssim_maps"] = 2 * sp * 4 if f > 1 else 2 * px * bps
     # float_ms_ssim: 5-level pyramid (9-tap low-pass, /2), maps on every level
-    mw, mh, prev = w, h, None
+    mw, mh = w, h
     for sc in range(5):
         if sc > 0:
             nw, nh = mw // 2 + (mw & 1), mh // 2 + (mh & 1)
@@ -142,15 +158,25 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def ncu_traffic(kernel: str, wname: str):
+_TRAFFIC = None
+
+
+def ncu_traffic(kernel: str | None, wname: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
-    capture of this workload (profiles/r01_traffic.json: {workload: {kernel: {"bytes": .., "frames": ..}}})."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        e = t[wname][kernel]
-        return e
-    except Exception:
+    capture of this workload (profiles/r02_traffic.json, else r01: {workload: {kernel: {"bytes": .., "frames": ..}}});
+    kernel=None returns the workload's whole table."""
+    global _TRAFFIC
+    if _TRAFFIC is None:
+        _TRAFFIC = {}
+        for nm in ("r01_traffic.json", "r02_traffic.json"):          # later rounds override, workload by workload
+            try:
+                _TRAFFIC.update(json.load(open(os.path.join(ROOT, "profiles", nm))))
+            except Exception:
+                pass
+    t = _TRAFFIC.get(wname)
+    if t is None:
         return None
+    return t if kernel is None else t.get(kernel)
 
 
 def measured_peaks() -> tuple:
@@ -264,14 +290,404 @@ def wl_dtype(wl) -> str:
 
 
 def bench_config(wl, wname, fps, n_gpus) -> dict:
+    chroma = wl["psnr"]
+    bps = 1 if wl["bpc"] == 8 else 2
+    mb = wl["pool"] * 2 * wl["w"] * wl["h"] * bps * (1.5 if chroma else 1.0) / 1e6
     return {"workload": f"{wname}: {wl['cfg']} -- {wl['w']}x{wl['h']} yuv420p {wl['bpc']}-bit, model {wl['model']}"
-                        + (" + psnr" if wl["psnr"] else "") + (" + float_ssim" if wl["ssim"] else "")
+                        + (" + psnr (y, cb, cr)" if wl["psnr"] else "") + (" + float_ssim" if wl["ssim"] else "")
                         + (" + float_ms_ssim" if wl["ms_ssim"] else ""),
             "frames_per_step_per_gpu": fps, "pool_frames_per_gpu": wl["pool"],
+            "planes": "Y, Cb, Cr (psnr=1 reads all three)" if chroma else "Y (every enabled feature reads luma only)",
             "l2_policy": "inputs larger than L2: each step streams the whole resident pool "
-                         f"({wl['pool']} frame pairs, {wl['pool'] * 2 * wl['w'] * wl['h'] * (1 if wl['bpc'] == 8 else 2) / 1e6:.0f} MB of luma) "
-                         "through the kernels",
+                         f"({wl['pool']} frame pairs, {mb:.0f} MB) through the kernels",
             "parallelism": f"frame-sharded x{n_gpus}, no collective"}
+
+
+# --------------------------------------------------------------------------------------------
+class Ctx:
+    """Per-process state shared by the measurements: ranks, the optional process group, helpers."""
+
+    def __init__(self, args):
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        self.numa_note = None
+
+    def init_dist(self):
+        if self.world > 1:
+            self.numa_note = bind_to_gpu_numa_node(self.local)
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max_over_ranks(self, v: float) -> float:
+        if self.dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{self.local}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+class Pool:
+    """P synthetic frame pairs: pinned on the host (e2e) and, optionally, resident in HBM (value)."""
+
+    def __init__(self, w, h, bpc, P, seed, chroma: bool, device: int, resident: bool = True):
+        from concurrent.futures import ThreadPoolExecutor
+        from pqa2_b200 import synth
+        from pqa2_b200.extractor import DeviceBuffer, pinned_empty
+        self.w, self.h, self.bpc, self.P, self.chroma = w, h, bpc, P, chroma
+        self.bps = 1 if bpc == 8 else 2
+        dtype = np.uint8 if bpc == 8 else np.uint16
+        shapes = [(h, w)] + ([((h + 1) // 2, (w + 1) // 2)] * 2 if chroma else [])
+        self.shapes = shapes
+        self.plane_bytes = [a * b * self.bps for a, b in shapes]
+        self.frame_bytes = sum(self.plane_bytes)
+        self.ref = [[pinned_empty(s, dtype) for s in shapes] for _ in range(P)]
+        self.dis = [[pinned_empty(s, dtype) for s in shapes] for _ in range(P)]
+
+        def fill(i):
+            rp, dp = synth.frame_pair(seed, i, w, h, bpc, chroma=chroma)
+            for k in range(len(shapes)):
+                self.ref[i][k][...] = rp[k]
+                self.dis[i][k][...] = dp[k]
+
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            list(ex.map(fill, range(P)))
+        self.dev = None
+        if resident:
+            self.dev = DeviceBuffer(2 * P * self.frame_bytes, device)
+            for i in range(P):
+                for clip, planes in ((0, self.ref[i]), (1, self.dis[i])):
+                    off = (2 * i + clip) * self.frame_bytes
+                    for k, p in enumerate(planes):
+                        self.dev.upload(off, p)
+                        off += self.plane_bytes[k]
+
+    def dev_planes(self, i: int, clip: int):
+        off = (2 * (i % self.P) + clip) * self.frame_bytes
+        out = []
+        for k, (ph, pw) in enumerate(self.shapes):
+            out.append((self.dev.ptr + off, pw * self.bps))
+            off += self.plane_bytes[k]
+        return out
+
+    def clip(self, n: int, offset: int = 0, stride: int = 1):
+        """A zero-copy engine.FrameSource of n frames cycling through the pinned pool."""
+        from pqa2_b200 import engine
+        pool = self
+
+        class PinnedClip(engine.FrameSource):
+            zero_copy = True
+
+            def __init__(self):
+                self.width, self.height, self.bpc = pool.w, pool.h, pool.bpc
+                self.chroma, self.nb_frames, self.fps = (420 if pool.chroma else 0), n, 30.0
+
+            def get(self, i, luma_only):
+                k = (offset + i * stride) % pool.P
+                return (pool.ref[k][:1], pool.dis[k][:1]) if luma_only else (pool.ref[k], pool.dis[k])
+
+        return PinnedClip()
+
+    def free(self):
+        if self.dev is not None:
+            self.dev.free()
+        self.ref = self.dis = None
+
+
+def measure_workload(cx: Ctx, wname: str, wl: dict, pool: Pool, steps: int, warmup: int, with_clocks: bool,
+                     with_e2e: bool) -> dict:
+    """Resident `value` (CUDA events on the compute stream), the per-kernel pass with the roofline of the top kernel, and the
+    host-buffer `e2e` of one workload on this rank's GPU."""
+    from pqa2_b200 import _lib as L
+    from pqa2_b200 import engine, model as M
+    from pqa2_b200.extractor import FeatureExtractor
+    args, local, world = cx.args, cx.local, cx.world
+    w, h, bpc = wl["w"], wl["h"], wl["bpc"]
+    bps = pool.bps
+    fps_step = args.frames_per_step or wl["frames_per_step"]
+    model = M.resolve_model(wl["model"])
+    opt = engine.EngineOptions(psnr=wl["psnr"], ssim=wl["ssim"], ms_ssim=wl["ms_ssim"], devices=(local,))
+    mask = engine.feature_mask(model, opt)
+    fx = FeatureExtractor(w, h, bpc, 420 if pool.chroma else 0, mask, local, vif_enhn_gain_limit=model.vif_enhn_gain_limit,
+                          adm_enhn_gain_limit=model.adm_enhn_gain_limit)
+    counter = [0]
+    # bytes of one frame of one clip that the enabled features actually read (luma only unless psnr / ssim stats want chroma)
+    uses_chroma = pool.chroma and bool(mask & (L.FEAT_PSNR_UV | L.FEAT_FFSSIM))
+    frame_bytes = pool.frame_bytes if uses_chroma else pool.plane_bytes[0]
+
+    def run_step():
+        for _ in range(fps_step):
+            i = counter[0]
+            fx.submit_device(i, pool.dev_planes(i, 0), pool.dev_planes(i, 1), L.FRAME_FIRST if i == 0 else 0)
+            counter[0] += 1
+
+    # ---- resident run: W warm-up steps, then exactly K timed steps
+    for _ in range(max(warmup, 3)):
+        run_step()
+    fx.flush()
+    sampler = ClockSampler(local) if with_clocks else None
+    cx.barrier()
+    fx.flush()
+    launches0 = fx.kernel_launches
+    if sampler:
+        sampler.start()
+    fx.timer_mark(0)
+    for _ in range(steps):
+        run_step()
+    fx.timer_mark(1)
+    fx.flush()
+    ms = fx.timer_elapsed_ms()
+    cx.barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = fx.kernel_launches - launches0
+    ms = cx.max_over_ranks(ms)
+    value = fps_step * steps * world / (ms / 1000.0)
+
+    # ---- per-kernel profile over the same region (events around every launch; a separate pass so the
+    #      event overhead stays out of `value`)
+    fx.set_profiling(True)
+    fx.kernel_profile(reset=True)
+    for _ in range(min(steps, 10)):
+        run_step()
+    fx.flush()
+    prof = fx.kernel_profile(reset=True)
+    fx.set_profiling(False)
+    peak, peak_src = measured_peaks()
+    B = fx.batch_frames
+    kernels = {}
+    for nm, (kms, cnt) in prof.items():
+        per_launch_ms = kms / cnt
+        by = kernel_bytes(nm, w, h, bps)
+        kernels[nm] = {"ms_per_launch": per_launch_ms, "launches": cnt,
+                       "gbps": (by * B / (per_launch_ms * 1e-3) / 1e9) if by else None}
+    tot_ms = sum(k["ms_per_launch"] for k in kernels.values()) or 1.0
+    top = max(kernels, key=lambda n: kernels[n]["ms_per_launch"]) if kernels else None
+    roofline = None
+    floor = 2 * frame_bytes                   # every input sample of the pair read once
+    if top:
+        by = kernel_bytes(top, w, h, bps)
+        ach = kernels[top]["gbps"]
+        tr = ncu_traffic(top, wname)
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": (ach / peak) if ach else None,
+                    "traffic": (tr["bytes"] * B / tr["frames"]) if tr else None,
+                    "traffic_source": (tr.get("source") if tr else None), "peak_source": peak_src,
+                    "pipe_note": (tr.get("pipe_note") if tr else None),
+                    "algorithmic_bytes_per_launch": by * B if by else None,
+                    "ms_per_launch": kernels[top]["ms_per_launch"], "frames_per_launch": B,
+                    "share_of_step": kernels[top]["ms_per_launch"] / tot_ms,
+                    "pipeline_floor_gbps": floor * value / world / 1e9,
+                    "pipeline_floor_frac": floor * value / world / 1e9 / peak}
+        # whole-pipeline DRAM traffic per frame pair (sum over the committed ncu capture of every kernel of this
+        # workload) against the floor of reading every input sample once
+        table = ncu_traffic(None, wname)
+        if table and all(k in table for k in kernels):
+            per_pair = sum(table[k]["bytes"] / table[k]["frames"] for k in kernels)
+            roofline["pipeline_dram_bytes_per_pair"] = per_pair
+            roofline["pipeline_dram_amplification"] = per_pair / floor
+        # The stencil kernels sit on the instruction-issue roof, not on HBM (DESIGN.md §4): report that roof too.
+        # Executed warp instructions per launch come from the committed ncu capture of this kernel; the rate is
+        # measured live (CUDA-event launch time); peak = SMs x 4 schedulers x 1 warp instruction per clock.
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        if tr and tr.get("warp_inst"):
+            wi = tr["warp_inst"] * B / tr["frames"]
+            peak_issue = 148 * 4 * sm_mhz * 1e6
+            roofline["issue"] = {"warp_instructions_per_launch": wi,
+                                 "achieved_gwarp_inst_s": wi / (kernels[top]["ms_per_launch"] * 1e-3) / 1e9,
+                                 "peak_gwarp_inst_s": peak_issue / 1e9,
+                                 "frac": wi / (kernels[top]["ms_per_launch"] * 1e-3) / peak_issue,
+                                 "thread_instructions_per_pixel": wi * 32 / (B * w * h)}
+    fx.close()
+
+    # ---- end to end through the public engine call: pinned host frames in, scores out
+    e2e = None
+    if with_e2e:
+        # one engine session (contexts stay alive between clips, as in a sweep of many clips); a step = one
+        # engine.analyze call over fps_step host frames: H2D of every plane the enabled features read, kernels, D2H of
+        # the feature rows, SVR fusion and pooling -- all inside the timed region.
+        k_e2e = max(1, min(steps, 10))
+        with engine.Engine() as sess:
+            for _ in range(2):
+                sess.analyze(pool.clip(fps_step), model, opt)                    # warm-up (allocations, first launches)
+            cx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                res = sess.analyze(pool.clip(fps_step), model, opt)
+            dt = time.perf_counter() - t0
+        dt = cx.max_over_ranks(dt)
+        n_e2e = fps_step * k_e2e
+        e2e = {"value": n_e2e * world / dt, "unit": "frames/s",
+               "h2d_bytes_per_step": int(2 * frame_bytes * fps_step),
+               "d2h_bytes_per_step": int((L.BV_RAW_WORDS * 8 + 64 * 8) * fps_step + 8 * fps_step),
+               "frames": n_e2e, "steps": k_e2e, "ms_per_step": 1000.0 * dt / k_e2e,
+               "timer": "host wall clock around K engine.analyze calls (pinned host frames -> H2D, kernels, feature D2H, "
+                        "SVR, pooling), max over ranks",
+               "pooled_vmaf_mean": res["pooled_metrics"]["vmaf"]["mean"]}
+        if cx.numa_note:
+            e2e["host_placement"] = cx.numa_note
+    return {"value": value, "ms_per_step": ms / steps, "steps": steps, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "e2e": e2e, "frames_per_launch": B,
+            "kernels": {k: {"ms_per_launch": round(v["ms_per_launch"], 5), "gbps": v["gbps"] and round(v["gbps"], 1),
+                            "frac_of_hbm_peak": v["gbps"] and round(v["gbps"] / peak, 4)} for k, v in kernels.items()}}
+
+
+def measure_sharded_4k(cx: Ctx, pool: Pool) -> dict:
+    """configs[2] as the north star partitions it: ONE 2160p 10-bit clip, contiguous frame chunks with a one-frame
+    lead-in, one rank per GPU, per-frame rows gathered on rank 0 (motion2 across the chunk borders, SVR and pooling
+    there).  Host frames in, pooled report out: an end-to-end, strong-scaling number."""
+    from pqa2_b200 import dist as D
+    from pqa2_b200 import engine, model as M
+    wl = WORKLOADS["4k-int"]
+    model = M.resolve_model(wl["model"])
+    opt = engine.EngineOptions(devices=(cx.local,))
+    n = cx.args.sharded_frames
+    clip = pool.clip(n)
+    times, res = [], None
+    with engine.Engine() as sess:
+        D.analyze_distributed(pool.clip(min(n, 64 * cx.world)), model, opt, device=cx.local, session=sess,
+                              svr_device=cx.local)                 # warm-up: contexts, first launches
+        for _ in range(2):
+            cx.barrier()
+            t0 = time.perf_counter()
+            r = D.analyze_distributed(clip, model, opt, device=cx.local, session=sess, svr_device=cx.local)
+            dt = time.perf_counter() - t0            # rank 0 returns after the gather, the SVR and the pooling
+            times.append(cx.max_over_ranks(dt))
+            res = r if r is not None else res
+        rec = None
+        if cx.rank == 0:
+            dt = min(times)
+            per_frame = 2 * pool.frame_bytes
+            rec = {"value": n / dt, "unit": "frames/s", "frames": n, "n_gpus": cx.world, "scaling": "strong",
+                   "seconds": dt, "runs": [round(t, 4) for t in times],
+                   "workload": f"configs[2]: ONE 3840x2160 yuv420p10le clip of {n} frames (a pinned pool of {pool.P} distinct "
+                               f"frame pairs, cycled), {wl['model']}, contiguous frame chunks + one-frame lead-in per rank, "
+                               "rows gathered on rank 0",
+                   "h2d_bytes_total": int(per_frame * (n + cx.world - 1)), "h2d_gbps_per_gpu": per_frame * n / cx.world / dt / 1e9,
+                   "pooled_vmaf_mean": res["pooled_metrics"]["vmaf"]["mean"],
+                   "timer": "host wall clock around dist.analyze_distributed (H2D of every frame, kernels, row gather, "
+                            "motion2 / SVR / pooling on rank 0); max over ranks, best of 2"}
+            if cx.world > 1:
+                # the same clip on rank 0's GPU alone: every per-frame value must be bit-identical (integer accumulators)
+                t0 = time.perf_counter()
+                one = sess.analyze(clip, model, opt)
+                rec["n1_same_run_fps"] = n / (time.perf_counter() - t0)
+                a, b = res["rows"].arr, one["rows"].arr
+                same_rows = all(np.array_equal(a[f], b[f]) for f in ("raw", "motion", "vif_scale", "adm_scale", "adm2"))
+                va = [fr["metrics"]["vmaf"] for fr in res["frames"]]
+                vb = [fr["metrics"]["vmaf"] for fr in one["frames"]]
+                m2a = [fr["metrics"]["integer_motion2"] for fr in res["frames"]]
+                m2b = [fr["metrics"]["integer_motion2"] for fr in one["frames"]]
+                rec["identical_to_n1"] = bool(same_rows and va == vb and m2a == m2b and
+                                              res["pooled_metrics"] == one["pooled_metrics"])
+                if not rec["identical_to_n1"]:
+                    log("[bench] ERROR: frame-sharded results differ from the single-GPU run; the sharded value is withdrawn")
+                    rec["value"] = None
+    cx.barrier()
+    return rec
+
+
+def measure_batch(cx: Ctx, pool: Pool) -> dict:
+    """configs[4]: a sweep of 64 clip pairs (300 frames of 1080p each), whole clips dealt over the ranks, one pooled
+    report per clip gathered on rank 0."""
+    from pqa2_b200 import dist as D
+    from pqa2_b200 import engine, model as M
+    model = M.resolve_model("vmaf_v0.6.1")
+    opt = engine.EngineOptions(devices=(cx.local,))
+    nclips, nfr = cx.args.batch_clips, BATCH_FRAMES
+    clips = [pool.clip(nfr, offset=5 * k, stride=1 + k % 3) for k in range(nclips)]
+    with engine.Engine() as sess:
+        sess.analyze(pool.clip(64), model, opt)                               # warm-up
+        cx.barrier()
+        t0 = time.perf_counter()
+        out = D.analyze_batch_distributed(clips, model, opt, device=cx.local, session=sess)
+        dt = cx.max_over_ranks(time.perf_counter() - t0)
+    if cx.rank != 0:
+        return None
+    errs = [o for o in out if o is None or "error" in o]
+    means = [o["pooled_metrics"]["vmaf"]["mean"] for o in out if o and "pooled_metrics" in o]
+    return {"value": (nclips * nfr / dt) if not errs else None, "unit": "frames/s", "clips": nclips, "frames_per_clip": nfr,
+            "clips_per_s": nclips / dt, "seconds": dt, "n_gpus": cx.world, "scaling": "strong", "failed_clips": len(errs),
+            "workload": f"configs[4]: {nclips} clips x {nfr} frames 1920x1080 8-bit (pinned pool of {pool.P} frame pairs, a "
+                        "different walk per clip), vmaf_v0.6.1, clip k on rank k % N, one session per rank",
+            "pooled_reports": len(means), "sum_of_pooled_vmaf_means": float(np.sum(np.array(means))) if means else None,
+            "h2d_bytes_total": int(2 * pool.plane_bytes[0] * nclips * nfr),
+            "timer": "host wall clock around dist.analyze_batch_distributed, max over ranks"}
+
+
+def measure_file_e2e(cx: Ctx, pool: Pool) -> dict:
+    """The call the reference makes (app/vmaf_analyzer.py:242): VMAFAnalyzer.analyze_videos(ref_path, dis_path) on a 300-frame
+    1080p yuv420p .y4m pair (configs[0]), all planes, with the reference's defaults (psnr / ssim stats files on)."""
+    from pqa2_b200 import yuvio
+    from pqa2_b200.vmaf_analyzer import VMAFAnalyzer
+    n = FILE_FRAMES
+    need = 2 * n * (pool.frame_bytes + 6) + (64 << 20)
+    base = None
+    for cand in ("/dev/shm", os.environ.get("TMPDIR") or "/tmp"):
+        try:
+            if os.path.isdir(cand) and shutil.disk_usage(cand).free > need:
+                base = cand
+                break
+        except OSError:
+            continue
+    if base is None:
+        return {"value": None, "note": "no scratch space for the clip pair"}
+    d = os.path.join(base, f"b200vmaf_bench_{os.getpid()}")
+    os.makedirs(d, exist_ok=True)
+    try:
+        rp, dp = os.path.join(d, "ref_1920x1080.y4m"), os.path.join(d, "dis_1920x1080.y4m")
+        t0 = time.perf_counter()
+        yuvio.write_y4m(rp, (pool.ref[i % pool.P] for i in range(n)), pool.w, pool.h, pool.bpc)
+        yuvio.write_y4m(dp, (pool.dis[i % pool.P] for i in range(n)), pool.w, pool.h, pool.bpc)
+        t_write = time.perf_counter() - t0
+        a = VMAFAnalyzer()
+        a.set_output_directory(d)
+        a.set_test_name("bench")
+        a.set_devices((cx.local,))
+        errs = []
+        a.error_occurred.connect(errs.append)
+        runs = []
+        res = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            res = a.analyze_videos(rp, dp, "vmaf_v0.6.1")
+            runs.append(time.perf_counter() - t0)
+            if res is None:
+                return {"value": None, "note": "analyze_videos failed: " + "; ".join(errs)}
+        ingest = "mmap + cudaHostRegister (page cache -> GPU, no CPU copy)" if getattr(a, "last_ingest", "") == "mapped" \
+            else "reader threads -> pinned ring"
+        return {"value": n / min(runs[1:]), "unit": "frames/s", "frames": n, "first_call_fps": n / runs[0],
+                "runs_s": [round(t, 4) for t in runs], "ingest": ingest, "clip_dir": base,
+                "bytes_read_per_call": int(2 * n * pool.frame_bytes),
+                "call": "VMAFAnalyzer.analyze_videos(ref.y4m, dis.y4m, 'vmaf_v0.6.1') with the reference defaults: libvmaf JSON + "
+                        "FFmpeg psnr and ssim stats files over Y, Cb, Cr; file read, H2D, kernels, D2H, SVR, pooling and the "
+                        "three output files inside the timed region; best of calls 2-3 (call 1 also creates the CUDA context)",
+                "vmaf_score": res["vmaf_score"], "psnr_log": bool(res["psnr_log"]), "ssim_log": bool(res["ssim_log"]),
+                "write_clip_pair_s": round(t_write, 2)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def two_gpus_in_one_process_check(cx: Ctx, pool: Pool) -> dict:
+    """The driver's GPU test box has one GPU, so tests/test_gpu_integer.py::test_two_gpus_in_one_process_match_one_gpu is
+    skipped there; with N >= 2 GPUs visible rank 0 runs the same check here: one process, one thread + context per GPU."""
+    from pqa2_b200 import engine, model as M
+    model = M.resolve_model("vmaf_v0.6.1")
+    clip = pool.clip(96)
+    one = engine.analyze(clip, model, engine.EngineOptions(devices=(0,)))
+    two = engine.analyze(clip, model, engine.EngineOptions(devices=(0, 1)))
+    same = [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in two["frames"]] and \
+        np.array_equal(one["rows"].arr["raw"], two["rows"].arr["raw"])
+    return {"frames": 96, "devices": [0, 1], "identical": bool(same)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -284,17 +700,18 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only (profiling runs)")
     ap.add_argument("--frames-per-step", type=int, default=0)
+    ap.add_argument("--sharded-frames", type=int, default=SHARDED_FRAMES)
+    ap.add_argument("--batch-clips", type=int, default=BATCH_CLIPS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cx = Ctx(args)
+    rank, world, local = cx.rank, cx.world, cx.local
 
     from pqa2_b200 import _lib as L
-    from pqa2_b200 import engine, model as M, synth
-    from pqa2_b200.extractor import DeviceBuffer, FeatureExtractor, pinned_empty
+    from pqa2_b200.extractor import FeatureExtractor
 
     wname = args.workload
     if wname == "auto":
@@ -315,194 +732,112 @@ def main() -> int:
             log(f"[bench] float extractors unavailable ({e}); measuring the integer workload 1080p-int instead")
             wname = "1080p-int"
             wl = WORKLOADS[wname]
+    cx.init_dist()
 
-    dist = None
-    numa_note = bind_to_gpu_numa_node(local) if world > 1 else None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    w, h, bpc = wl["w"], wl["h"], wl["bpc"]
-    bps = 1 if bpc == 8 else 2
-    fps_step = args.frames_per_step or wl["frames_per_step"]
-    P = wl["pool"]
-    model = M.resolve_model(wl["model"])
-    opt = engine.EngineOptions(psnr=wl["psnr"], ssim=wl["ssim"], ms_ssim=wl["ms_ssim"], devices=(local,))
-    mask = engine.feature_mask(model, opt)
-
-    # ---- synthetic clip: P frame pairs (luma only: every enabled feature reads luma), pinned on the
-    #      host (e2e) and resident in HBM (value)
+    # ---- headline workload
     t0 = time.perf_counter()
-    plane = w * h * bps
-    dtype = np.uint8 if bpc == 8 else np.uint16
-    host_ref = [pinned_empty((h, w), dtype) for _ in range(P)]
-    host_dis = [pinned_empty((h, w), dtype) for _ in range(P)]
-    dev = DeviceBuffer(2 * P * plane, local)
-    for i in range(P):
-        rp, dp = synth.frame_pair(100 + rank, i, w, h, bpc, chroma=False)
-        host_ref[i][...] = rp[0]
-        host_dis[i][...] = dp[0]
-        dev.upload((2 * i) * plane, host_ref[i])
-        dev.upload((2 * i + 1) * plane, host_dis[i])
+    pool = Pool(wl["w"], wl["h"], wl["bpc"], wl["pool"], 100 + rank, wl["psnr"], local)
     if rank == 0:
-        log(f"[bench] synthesised {P} frame pairs {w}x{h} {bpc}-bit in {time.perf_counter() - t0:.1f}s")
+        log(f"[bench] synthesised {wl['pool']} frame pairs {wl['w']}x{wl['h']} {wl['bpc']}-bit in {time.perf_counter() - t0:.1f}s")
+    head = measure_workload(cx, wname, wl, pool, args.steps, args.warmup, True, not args.no_e2e)
+    fps_step = args.frames_per_step or wl["frames_per_step"]
+    if rank == 0:
+        log(f"[bench] {wname}: {head['value']:.0f} fps resident" + (f", {head['e2e']['value']:.0f} e2e" if head["e2e"] else ""))
 
-    fx = FeatureExtractor(w, h, bpc, 0, mask, local, vif_enhn_gain_limit=model.vif_enhn_gain_limit,
-                          adm_enhn_gain_limit=model.adm_enhn_gain_limit)
-    pitch = w * bps
-    counter = [0]
+    extras = not args.no_extras and args.workload == "auto"
+    workloads, sharded, batch, file_e2e, twogpu = {}, None, None, None, None
+    pools = {wname: pool}
 
-    def run_step():
-        for _ in range(fps_step):
-            i = counter[0]
-            k = i % P
-            fx.submit_device(i, [(dev.ptr + (2 * k) * plane, pitch)], [(dev.ptr + (2 * k + 1) * plane, pitch)],
-                             L.FRAME_FIRST if i == 0 else 0)
-            counter[0] += 1
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(v: float) -> float:
-        if dist is None:
-            return v
-        import torch
-        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- resident run: W warm-up steps, then exactly K timed steps
-    for _ in range(max(args.warmup, 3)):
-        run_step()
-    fx.flush()
-    sampler = ClockSampler(local)
-    barrier()
-    fx.flush()
-    launches0 = fx.kernel_launches
-    sampler.start()
-    fx.timer_mark(0)
-    for _ in range(args.steps):
-        run_step()
-    fx.timer_mark(1)
-    fx.flush()
-    ms = fx.timer_elapsed_ms()
-    barrier()
-    clocks = sampler.stop()
-    launches = fx.kernel_launches - launches0
-    ms = max_over_ranks(ms)
-    total_frames = fps_step * args.steps * world
-    value = total_frames / (ms / 1000.0)
-
-    # ---- per-kernel profile over the same region (events around every launch; a separate pass so the
-    #      event overhead stays out of `value`)
-    fx.set_profiling(True)
-    fx.kernel_profile(reset=True)
-    for _ in range(min(args.steps, 10)):
-        run_step()
-    fx.flush()
-    prof = fx.kernel_profile(reset=True)
-    fx.set_profiling(False)
-    results_sample = fx.fetch(0, 1)
-    peak, peak_src = measured_peaks()
-    B = fx.batch_frames
-    kernels = {}
-    for nm, (kms, cnt) in prof.items():
-        per_launch_ms = kms / cnt
-        by = kernel_bytes(nm, w, h, bps)
-        kernels[nm] = {"ms_per_launch": per_launch_ms, "launches": cnt,
-                       "gbps": (by * B / (per_launch_ms * 1e-3) / 1e9) if by else None}
-    tot_ms = sum(k["ms_per_launch"] for k in kernels.values()) or 1.0
-    top = max(kernels, key=lambda n: kernels[n]["ms_per_launch"]) if kernels else None
-    roofline = None
-    if top:
-        by = kernel_bytes(top, w, h, bps)
-        ach = kernels[top]["gbps"]
-        tr = ncu_traffic(top, wname)
-        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None,
-                    "traffic": (tr["bytes"] * B / tr["frames"]) if tr else None,
-                    "traffic_source": (tr.get("source") if tr else None), "peak_source": peak_src,
-                    "pipe_note": (tr.get("pipe_note") if tr else None),
-                    "algorithmic_bytes_per_launch": by * B if by else None,
-                    "ms_per_launch": kernels[top]["ms_per_launch"], "frames_per_launch": B,
-                    "share_of_step": kernels[top]["ms_per_launch"] / tot_ms,
-                    "pipeline_floor_gbps": 2 * plane * value / world / 1e9,
-                    "pipeline_floor_frac": 2 * plane * value / world / 1e9 / peak}
-        # The stencil kernels sit on the instruction-issue roof, not on HBM: report that roof too.
-        # Executed warp instructions per launch come from the committed ncu capture of this kernel; the rate is
-        # measured live (CUDA-event launch time); peak = SMs x 4 schedulers x 1 warp instruction per clock.
-        if tr and tr.get("warp_inst") and clocks.get("sm_mhz"):
-            wi = tr["warp_inst"] * B / tr["frames"]
-            peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
-            roofline["issue"] = {"warp_instructions_per_launch": wi,
-                                 "achieved_gwarp_inst_s": wi / (kernels[top]["ms_per_launch"] * 1e-3) / 1e9,
-                                 "peak_gwarp_inst_s": peak_issue / 1e9,
-                                 "frac": wi / (kernels[top]["ms_per_launch"] * 1e-3) / peak_issue,
-                                 "thread_instructions_per_pixel": wi * 32 / (B * w * h)}
-    fx.close()
-
-    # ---- end to end through the public engine call: pinned host frames in, scores out
-    e2e = None
-    if not args.no_e2e:
-        class PinnedClip(engine.FrameSource):
-            zero_copy = True
-
-            def __init__(self, n):
-                self.width, self.height, self.bpc, self.chroma, self.nb_frames, self.fps = w, h, bpc, 0, n, 30.0
-
-            def get(self, i, luma_only):
-                return [host_ref[i % P]], [host_dis[i % P]]
-
-        # one engine session (contexts + pinned rings stay alive between clips, as in a sweep of many clips);
-        # a step = one engine.analyze call over fps_step host frames: H2D of every frame, kernels, D2H of the
-        # feature rows, SVR fusion and pooling -- all inside the timed region.
-        k_e2e = max(1, min(args.steps, 10))
-        with engine.Engine() as sess:
-            for _ in range(2):
-                sess.analyze(PinnedClip(fps_step), model, opt)                    # warm-up (allocations, first launches)
-            barrier()
+    def get_pool(name, seed, chroma):
+        if name not in pools:
+            w_ = WORKLOADS[name]
             t0 = time.perf_counter()
-            for _ in range(k_e2e):
-                res = sess.analyze(PinnedClip(fps_step), model, opt)
-            dt = time.perf_counter() - t0
-        dt = max_over_ranks(dt)
-        n_e2e = fps_step * k_e2e
-        e2e = {"value": n_e2e * world / dt, "unit": "frames/s",
-               "h2d_bytes_per_step": int(2 * plane * fps_step),
-               "d2h_bytes_per_step": int((L.BV_RAW_WORDS * 8 + 64 * 8) * fps_step + 8 * fps_step),
-               "frames": n_e2e, "steps": k_e2e, "ms_per_step": 1000.0 * dt / k_e2e,
-               "timer": "host wall clock around K engine.analyze calls (pinned host frames -> H2D, kernels, feature D2H, "
-                        "SVR, pooling), max over ranks",
-               "pooled_vmaf_mean": res["pooled_metrics"]["vmaf"]["mean"]}
-        if numa_note:
-            e2e["host_placement"] = numa_note
+            pools[name] = Pool(w_["w"], w_["h"], w_["bpc"], w_["pool"], seed, chroma, local)
+            if rank == 0:
+                log(f"[bench] synthesised {w_['pool']} frame pairs {w_['w']}x{w_['h']} {w_['bpc']}-bit in {time.perf_counter() - t0:.1f}s")
+        return pools[name]
+
+    def guarded(label, fn):
+        try:
+            return fn()
+        except Exception as e:          # noqa: BLE001  (an extra record never costs the headline line)
+            log(f"[bench] {label} failed: {type(e).__name__}: {e}")
+            if world > 1:
+                raise                   # ranks would lose step with each other: fail loudly instead of hanging
+            return {"value": None, "error": f"{type(e).__name__}: {e}"}
+
+    if extras:
+        steps_x = max(2, min(args.steps, 10))
+        if world == 1:
+            # the integer v0.6.1 configurations of BASELINE's metric, each with its own roofline and CPU baseline
+            r = guarded("1080p-int", lambda: measure_workload(cx, "1080p-int", WORKLOADS["1080p-int"], pool, steps_x,
+                                                              args.warmup, False, not args.no_e2e))
+            workloads["1080p-int"] = r
+            log(f"[bench] 1080p-int: {r.get('value')} fps resident")
+            file_e2e = guarded("file_e2e", lambda: measure_file_e2e(cx, pool))
+            log(f"[bench] file_e2e: {file_e2e}")
+        batch = guarded("batch", lambda: measure_batch(cx, pool))
+        if rank == 0:
+            log(f"[bench] batch: {batch}")
+        if world > 1 and rank == 0 and lib.bv_device_count() >= 2:
+            twogpu = guarded("two_gpus_in_one_process", lambda: two_gpus_in_one_process_check(cx, pool))
+        cx.barrier()
+        pool.free()                     # the 4K pool wants the pinned memory and HBM
+        p4 = get_pool("4k-int", 7, False)           # the same clip on every rank
+        if world == 1:
+            r = guarded("4k-int", lambda: measure_workload(cx, "4k-int", WORKLOADS["4k-int"], p4, steps_x, args.warmup,
+                                                           False, not args.no_e2e))
+            workloads["4k-int"] = r
+            log(f"[bench] 4k-int: {r.get('value')} fps resident")
+        sharded = guarded("sharded_4k", lambda: measure_sharded_4k(cx, p4))
+        if rank == 0:
+            log(f"[bench] sharded_4k: {sharded}")
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        if cx.dist is not None:
+            cx.dist.destroy_process_group()
         return 0
 
     base = None
     if not args.no_cpu_baseline and world == 1:
-        try:
-            base = cpu_baseline(wl)
-        except Exception as e:          # the baseline is a report, never a reason to lose the GPU numbers
-            base = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        def cb(w_):
+            try:
+                return cpu_baseline(w_)
+            except Exception as e:          # the baseline is a report, never a reason to lose the GPU numbers
+                return {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        base = cb(wl)
+        for nm, rec in workloads.items():
+            if rec.get("value"):
+                rec["cpu_baseline"] = cb(WORKLOADS[nm])
+    for nm, rec in workloads.items():
+        if "roofline" in rec:
+            rec["config"] = bench_config(WORKLOADS[nm], nm, args.frames_per_step or WORKLOADS[nm]["frames_per_step"], world)
+            rec["dtype"] = wl_dtype(WORKLOADS[nm])
+            rec["unit"] = "frames/s"
 
-    out = {"metric": "vmaf_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-           "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+    out = {"metric": "vmaf_frames_per_sec", "value": head["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": wl_dtype(wl), "data": "synthetic",
-           "config": bench_config(wl, wname, fps_step, world), "clocks": clocks, "e2e": e2e,
-           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": base,
-           "kernels": {k: {"ms_per_launch": round(v["ms_per_launch"], 5), "gbps": v["gbps"] and round(v["gbps"], 1),
-                           "frac_of_hbm_peak": v["gbps"] and round(v["gbps"] / peak, 4)} for k, v in kernels.items()},
+           "config": bench_config(wl, wname, fps_step, world), "clocks": head["clocks"], "e2e": head["e2e"],
+           "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": base,
+           "kernels": head["kernels"],
            "published_reference_fps": "23-26 fps (1080p, libvmaf n_threads=4, decode included; BASELINE.md §1)"}
+    if workloads:
+        out["workloads"] = workloads
+    if sharded is not None:
+        out["sharded_4k"] = sharded
+    if batch is not None:
+        out["batch"] = batch
+    extra = {}
+    if file_e2e is not None:
+        extra["file_e2e"] = file_e2e
+    if twogpu is not None:
+        extra["two_gpus_in_one_process"] = twogpu
+    if extra:
+        out["extra"] = extra
     print(json.dumps(out), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    if cx.dist is not None:
+        cx.dist.destroy_process_group()
     return 0
 
 

@@ -100,6 +100,12 @@ const char *bv_last_error(bv_ctx *);     /* ctx may be NULL: error of the last f
 /* cudaHostAlloc / cudaFreeHost wrappers so callers can stage frames in pinned memory. */
 int  bv_pinned_alloc(void **p, size_t n);
 int  bv_pinned_free(void *p);
+/* cudaHostRegister / cudaHostUnregister of caller-owned memory -- e.g. an mmap of a raw .y4m / .yuv clip, so that
+ * bv_submit's cudaMemcpyAsync reads the page cache directly instead of a staging copy (the reference lets ffmpeg
+ * read the two input files itself, app/vmaf_analyzer.py:415-416).  read_only != 0 asks for a read-only registration
+ * (PROT_READ mappings).  Returns BV_ERR_CUDA when the platform refuses; callers then fall back to a pinned ring. */
+int  bv_host_register(void *p, size_t n, int read_only);
+int  bv_host_unregister(void *p);
 /* cudaMalloc / cudaFree / blocking H2D copy on `device`, for callers that keep clips resident in HBM
  * and score them with bv_submit_device (the resident mode of bench.py). */
 int  bv_device_alloc(int device, void **p, size_t n);

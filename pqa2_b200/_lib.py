@@ -65,7 +65,7 @@ class BvFrameFeatures(C.Structure):
 
 EXPORTS = (
     "bv_abi_version", "bv_device_count", "bv_create", "bv_destroy", "bv_last_error", "bv_pinned_alloc",
-    "bv_pinned_free", "bv_device_alloc", "bv_device_free", "bv_device_upload", "bv_sizeof_frame_features",
+    "bv_pinned_free", "bv_host_register", "bv_host_unregister", "bv_device_alloc", "bv_device_free", "bv_device_upload", "bv_sizeof_frame_features",
     "bv_submit", "bv_submit_device", "bv_wait_uploads", "bv_flush", "bv_frames_done", "bv_fetch", "bv_cancel",
     "bv_reset", "bv_kick", "bv_batch_frames",
     "bv_kernel_launches", "bv_set_profiling", "bv_kernel_slots", "bv_kernel_name", "bv_kernel_ms", "bv_kernel_count",
@@ -105,6 +105,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.bv_last_error.restype = C.c_char_p
     L.bv_pinned_alloc.argtypes = [pp, sz]
     L.bv_pinned_free.argtypes = [vp]
+    L.bv_host_register.argtypes = [vp, sz, i]
+    L.bv_host_unregister.argtypes = [vp]
     L.bv_device_alloc.argtypes = [i, pp, sz]
     L.bv_device_free.argtypes = [i, vp]
     L.bv_device_upload.argtypes = [i, vp, vp, sz]

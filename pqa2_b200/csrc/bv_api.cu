@@ -556,6 +556,19 @@ int bv_pinned_alloc(void **p, size_t n)
 }
 int bv_pinned_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? 0 : BV_ERR_CUDA; }
 
+int bv_host_register(void *p, size_t n, int read_only)
+{
+    if (!p || n == 0) return BV_ERR_ARG;
+    cudaError_t e = cudaHostRegister(p, n, read_only ? cudaHostRegisterReadOnly : cudaHostRegisterDefault);
+    if (e != cudaSuccess) { fail(nullptr, BV_ERR_CUDA, "cudaHostRegister", e); cudaGetLastError(); return BV_ERR_CUDA; }
+    return 0;
+}
+int bv_host_unregister(void *p)
+{
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return BV_ERR_CUDA; }
+    return 0;
+}
+
 int bv_device_alloc(int device, void **p, size_t n)
 {
     if (!p) return BV_ERR_ARG;

@@ -20,14 +20,22 @@ def rank_range(n_frames: int, rank: int, world: int, first: int = 0):
     return (first + r[rank][0], first + r[rank][1])
 
 
-def _default_shard_fn(src, model, opt, device, start, end, mask):
+def _default_shard_fn(src, model, opt, device, start, end, mask, session=None):
     rows = engine.Rows(src.nb_frames)
     errors, holders = [], []
-    engine._run_shard(src, model, opt, device, start, end, mask, rows, None, threading.Event(), errors, holders)
+    engine._run_shard(src, model, opt, device, start, end, mask, rows, None, threading.Event(), errors, holders,
+                      session)
     for kind, e in errors:
         if kind == "error":
             raise e
     return ("block", start, rows.arr[start:end].copy())        # one structured array per shard (~1.3 KB/frame)
+
+
+def _world(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
 
 
 def max_over_ranks(value: float, group=None, device=None) -> float:
@@ -41,20 +49,29 @@ def max_over_ranks(value: float, group=None, device=None) -> float:
 
 
 def analyze_distributed(src, model, opt: engine.EngineOptions | None = None, device: int = 0, group=None,
-                        shard_fn=None, svr_device=None):
+                        shard_fn=None, svr_device=None, session: "engine.Engine | None" = None):
     """Call on every rank.  Returns the libvmaf log dict on rank 0 and None elsewhere.
 
     ``shard_fn(src, model, opt, device, start, end, mask) -> {frame_index: row}`` computes one shard
-    (default: the CUDA extractors on ``device``); the CPU tests inject a stub."""
-    import torch.distributed as dist
+    (default: the CUDA extractors on ``device``); the CPU tests inject a stub.  ``session`` keeps this rank's
+    CUDA context alive between clips.  Without an initialised process group the call is the world-size-1 case."""
     opt = opt or engine.EngineOptions()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = _world(group)
     n = src.nb_frames
     start, end = rank_range(n, rank, world)
     mask = engine.feature_mask(model, opt)
-    mine = (shard_fn or _default_shard_fn)(src, model, opt, device, start, end, mask) if end > start else {}
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(mine, gathered, dst=0, group=group)
+    if end <= start:
+        mine = {}
+    elif shard_fn is not None:
+        mine = shard_fn(src, model, opt, device, start, end, mask)
+    else:
+        mine = _default_shard_fn(src, model, opt, device, start, end, mask, session)
+    if world > 1:
+        import torch.distributed as dist
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(mine, gathered, dst=0, group=group)
+    else:
+        gathered = [mine]
     if rank != 0:
         return None
     if all(isinstance(p, tuple) or not p for p in gathered):
@@ -72,6 +89,45 @@ def analyze_distributed(src, model, opt: engine.EngineOptions | None = None, dev
         missing = [i for i, r in enumerate(rows) if r is None]
     if missing:
         raise RuntimeError(f"frames missing after the gather: {missing[:8]}...")
-    frames = engine.build_frames(rows, model, opt, svr_device)
-    return {"version": report.VERSION, "frames": frames, "pooled_metrics": report.pooled_metrics(frames),
+    pooled_out: dict = {}
+    frames = engine.build_frames(rows, model, opt, svr_device, pooled_out)
+    return {"version": report.VERSION, "frames": frames,
+            "pooled_metrics": pooled_out.get("pooled") or report.pooled_metrics(frames),
             "aggregate_metrics": {}, "rows": rows, "model": model.name, "n_frames": n, "world_size": world}
+
+
+def analyze_batch_distributed(clips: list, model, opt: engine.EngineOptions | None = None, device: int = 0, group=None,
+                              session: "engine.Engine | None" = None, summarize=None):
+    """Many clips over the ranks (BASELINE.json configs[4]; the one-process-per-GPU twin of engine.analyze_batch):
+    whole clips are the unit, clip k runs on rank ``k % world`` through that rank's session, and one small summary per
+    clip -- by default its pooled report -- is gathered on rank 0, in input order.  No lead-in frames, no collective on
+    the data path.  Returns the list on rank 0, None elsewhere; a failed clip yields ``{"error": str}``."""
+    from dataclasses import replace
+    opt = replace(opt or engine.EngineOptions(), devices=(device,))
+    rank, world = _world(group)
+    summarize = summarize or (lambda log: {k: v for k, v in log.items() if k not in ("frames", "rows")})
+    own = session is None
+    sess = session or engine.Engine()
+    mine = {}
+    try:
+        for k in range(rank, len(clips), world):
+            try:
+                mine[k] = summarize(sess.analyze(clips[k], model, opt))
+            except Exception as e:            # noqa: BLE001  (the reference's per-clip error convention)
+                mine[k] = {"error": str(e)}
+    finally:
+        if own:
+            sess.close()
+    if world > 1:
+        import torch.distributed as dist
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(mine, gathered, dst=0, group=group)
+    else:
+        gathered = [mine]
+    if rank != 0:
+        return None
+    out = [None] * len(clips)
+    for part in gathered:
+        for k, v in part.items():
+            out[k] = v
+    return out

@@ -39,6 +39,7 @@ class EngineOptions:
     batch_frames: int = 0
     svr_on_device: bool = True
     extra_features: int = 0          # extra _lib.FEAT_* bits
+    reader_threads: int = 4          # file readers per shard when clips cannot be mapped (pinned-ring path)
     float_motion: bool = False       # `feature=name=motion` (app/vmaf_analyzer.py:388-402): libvmaf's float motion
                                      # extractor next to the model's own features -> `motion`, `motion2` in the log
 
@@ -63,7 +64,12 @@ class FrameSource:
 
 
 class FileSource(FrameSource):
-    def __init__(self, ref_info, dis_info):
+    """A reference / distorted pair of clip files.  Raw clips (.y4m / planar .yuv) are mapped and registered with
+    CUDA when the platform allows it (``yuvio.MappedClip``): the shards then hand page-cache views straight to
+    ``bv_submit`` (``zero_copy``).  Otherwise -- and for containers -- frames are read into a pinned ring by
+    reader threads (``_Prefetcher``)."""
+
+    def __init__(self, ref_info, dis_info, mapped: bool | None = None):
         from .yuvio import ClipReader
         self._ri, self._di = ref_info, dis_info
         self.width, self.height, self.bpc, self.chroma = ref_info.width, ref_info.height, ref_info.bpc, ref_info.chroma
@@ -71,9 +77,39 @@ class FileSource(FrameSource):
         self.fps = dis_info.fps or ref_info.fps or 30.0
         self._r = self._d = None
         self._ClipReader = ClipReader
+        self._want_mapped = mapped
+        self._maps = None                     # (MappedClip ref, MappedClip dis) shared by every shard, or False
+        self._lock = threading.Lock()
+        self.sequential = getattr(ref_info, "decoder", "raw") != "raw" or getattr(dis_info, "decoder", "raw") != "raw"
+        self.parallel_reads = not self.sequential     # raw files: any frame can be read by any reader thread
+
+    def _mapped(self):
+        with self._lock:
+            if self._maps is None:
+                self._maps = False
+                if self._want_mapped is not False and not self.sequential:
+                    from .yuvio import MappedClip
+                    r = MappedClip.open(self._ri)
+                    d = MappedClip.open(self._di) if r is not None else None
+                    if r is not None and d is not None:
+                        self._maps = (r, d)
+                    elif r is not None:
+                        r.close()
+            return self._maps
+
+    @property
+    def zero_copy(self) -> bool:
+        return bool(self._mapped())
+
+    def get(self, i, luma_only):
+        r, d = self._maps
+        return r.planes(i, luma_only), d.planes(i, luma_only)
 
     def open(self):
-        s = FileSource(self._ri, self._di)
+        if self._mapped():
+            return self                       # views of the shared mappings: nothing per thread
+        s = FileSource(self._ri, self._di, mapped=False)
+        s._maps = False
         s._r, s._d = self._ClipReader(self._ri), self._ClipReader(self._di)
         return s
 
@@ -81,10 +117,90 @@ class FileSource(FrameSource):
         for r in (self._r, self._d):
             if r:
                 r.close()
+        self._r = self._d = None
+
+    def release(self):
+        """Drop the shared mappings (after the last analyze() on this source)."""
+        with self._lock:
+            if self._maps:
+                for m in self._maps:
+                    m.close()
+            self._maps = None
 
     def read_into(self, i, ref_planes, dis_planes, luma_only):
         self._r.read_into(i, ref_planes, luma_only)
         self._d.read_into(i, dis_planes, luma_only)
+
+
+class _Prefetcher:
+    """Reader threads that fill a pinned ring ahead of the submitting thread (file reads release the GIL).  Ring slot
+    ``o % len(ring)`` may be filled for ordinal ``o`` once ``release(limit)`` has promised that every ordinal below
+    ``limit - len(ring)`` was uploaded."""
+
+    def __init__(self, src: FrameSource, first_handle, ring, frame_ids, luma_only: bool, n_threads: int):
+        self.ring, self.ids, self.luma_only = ring, frame_ids, luma_only
+        self.cond = threading.Condition()
+        self.next, self.limit, self.stop = 0, min(len(ring), len(frame_ids)), False
+        self.filled = [False] * len(frame_ids)
+        self.end_at, self.error = None, None
+        self.handles = [first_handle] + [src.open() for _ in range(max(1, n_threads) - 1)]
+        self.threads = [threading.Thread(target=self._work, args=(h,), daemon=True) for h in self.handles]
+        for t in self.threads:
+            t.start()
+
+    def _work(self, handle):
+        while True:
+            with self.cond:
+                while not self.stop and (self.next >= self.limit or self.next >= len(self.ids)):
+                    if self.next >= len(self.ids):
+                        return
+                    self.cond.wait()
+                if self.stop:
+                    return
+                o = self.next
+                self.next += 1
+            rp, dp = self.ring[o % len(self.ring)]
+            try:
+                handle.read_into(self.ids[o], rp, dp, self.luma_only)
+            except EndOfClip:
+                with self.cond:
+                    self.end_at = o if self.end_at is None else min(self.end_at, o)
+                    self.stop = True
+                    self.cond.notify_all()
+                return
+            except Exception as e:            # noqa: BLE001  (re-raised on the submitting thread)
+                with self.cond:
+                    self.error = e
+                    self.stop = True
+                    self.cond.notify_all()
+                return
+            with self.cond:
+                self.filled[o] = True
+                self.cond.notify_all()
+
+    def get(self, o: int):
+        with self.cond:
+            while not self.filled[o]:
+                if self.error is not None:
+                    raise self.error
+                if self.end_at is not None and o >= self.end_at:
+                    raise EndOfClip(f"clip ends at ordinal {self.end_at}")
+                self.cond.wait()
+        return self.ring[o % len(self.ring)]
+
+    def release(self, limit: int):
+        with self.cond:
+            self.limit = max(self.limit, min(limit, len(self.ids)))
+            self.cond.notify_all()
+
+    def close(self, own_first: bool = False):
+        with self.cond:
+            self.stop = True
+            self.cond.notify_all()
+        for t in self.threads:
+            t.join()
+        for h in self.handles[0 if own_first else 1:]:
+            h.close()
 
 
 class SynthSource(FrameSource):
@@ -147,6 +263,7 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
                session: "Engine | None" = None, shard: int = 0, lead_in: bool | None = None):
     handle = None
     fx = None
+    pre = None
     try:
         handle = src.open()
         luma_only = not (mask & (L.FEAT_PSNR_UV | L.FEAT_FFSSIM)) or src.chroma in (0, 400)
@@ -174,21 +291,26 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
                 [([pinned_empty(s, dtype) for s in shapes], [pinned_empty(s, dtype) for s in shapes]) for _ in range(2 * B)]
         lead = (1 if start > 0 else 0) if lead_in is None else (1 if lead_in and start > 0 else 0)
         ordinal = 0
+        ids = list(range(start - lead, end))
+        if not zero_copy:
+            # raw files: several readers (page-cache copies run beside each other); a decoder is one sequential stream
+            n_readers = opt.reader_threads if getattr(src, "parallel_reads", False) else 1
+            pre = _Prefetcher(src, handle, ring, ids, luma_only, n_readers)
         # pictures large enough for a reduced group size are upload-bound over PCIe: only there does a short last
         # launch shorten the call; at <= 1440p the GPU is the bottleneck and short groups would only run less efficiently
         tail_split = B < L.BV_MAX_BATCH
-        for i in range(start - lead, end):
+        for i in ids:
             if cancel.is_set():
                 fx.cancel()
                 raise _Cancelled()
             if zero_copy:
-                rp, dp = handle.get(i, luma_only)     # caller-owned (pinned) planes, valid until we return
+                rp, dp = handle.get(i, luma_only)     # caller-owned (pinned / registered) planes, valid until we return
             else:
                 if ordinal and ordinal % B == 0:
-                    fx.wait_uploads()       # the half of the ring we are about to overwrite is free again
-                rp, dp = ring[ordinal % len(ring)]
+                    fx.wait_uploads()       # everything submitted so far is on the GPU: those ring slots are free again
+                    pre.release(ordinal + len(ring))
                 try:
-                    handle.read_into(i, rp, dp, luma_only)
+                    rp, dp = pre.get(ordinal)
                 except EndOfClip:
                     # the container promised more frames than it decodes to (its frame count is an estimate): the
                     # clip ends here, as it does for ffmpeg + libvmaf, which stop at the shorter input
@@ -224,6 +346,8 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
         errors.append(("error", e))
         cancel.set()                  # a failed shard stops its siblings instead of letting them run to the end
     finally:
+        if pre is not None:
+            pre.close()
         if fx is not None and session is None:
             fx.close()
         if handle is not None and handle is not src:

@@ -93,6 +93,10 @@ class VMAFAnalyzer(QObject):
         self.psnr_enabled = True
         self.ssim_enabled = True
         self.devices = None                  # None -> all visible GPUs
+        # CUDA contexts (one per GPU and picture geometry) stay alive between analyses of this analyzer: the reference
+        # pays an ffmpeg process start per call (:446), a second call here starts on warm contexts
+        self._engine = engine.Engine()
+        self.last_ingest = None              # "mapped" (mmap + cudaHostRegister) or "ring" (reader threads), for reports
 
     # ---- option setters (reference :44-137) --------------------------------------------------
     def set_options_from_manager(self, options_manager):
@@ -131,6 +135,10 @@ class VMAFAnalyzer(QObject):
     def set_devices(self, devices):
         """GPU ordinals to shard frames over (extension; the reference has `threads` instead)."""
         self.devices = tuple(devices) if devices is not None else None
+
+    def close(self):
+        """Free the CUDA contexts kept between analyses (also happens when the analyzer is collected)."""
+        self._engine.close()
 
     def terminate_analysis(self):
         """Cancel the running analysis (reference :139-151 kills the ffmpeg child)."""
@@ -228,7 +236,11 @@ class VMAFAnalyzer(QObject):
                 self.analysis_progress.emit(pct)
 
         self.status_update.emit(f"Scoring {src.nb_frames} frames on {len(devices)} GPU(s)")
-        res = engine.analyze(src, vm, opt, progress_cb=on_progress, cancel=self._cancel)
+        try:
+            self.last_ingest = "mapped" if src.zero_copy else "ring"
+            res = self._engine.analyze(src, vm, opt, progress_cb=on_progress, cancel=self._cancel)
+        finally:
+            src.release()
         if res is None or self._terminate_requested:
             self.status_update.emit("VMAF analysis terminated by user")      # reference :514-518
             return None

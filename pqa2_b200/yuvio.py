@@ -249,6 +249,78 @@ class ClipReader:
                 raise EOFError(f"{self.info.path}: short read at frame {i}")
 
 
+class MappedClip:
+    """A raw clip mapped into memory and registered with CUDA (``bv_host_register``): frame planes are numpy views
+    of the page cache, and ``bv_submit`` DMAs them to the GPU without a CPU copy.  ``MappedClip.open`` returns None
+    when the file cannot be mapped or the platform refuses the registration (the caller then reads through a pinned
+    ring, ``ClipReader``)."""
+
+    def __init__(self, info: ClipInfo, mm, base_addr: int, registered_len: int):
+        self.info, self._mm, self._addr, self._len = info, mm, base_addr, registered_len
+        self._dtype = np.uint8 if info.bpc == 8 else np.dtype("<u2")
+        self._buf = np.frombuffer(mm, dtype=np.uint8)
+        self._shapes = info.plane_shapes()
+
+    @classmethod
+    def open(cls, info: ClipInfo, min_bytes: int = 1 << 20):
+        import ctypes
+        import mmap
+        from . import _lib as L
+        if getattr(info, "decoder", "raw") != "raw" or info.nb_frames < 1:
+            return None
+        size = os.path.getsize(info.path)
+        if size < min_bytes:
+            return None
+        lib = L.load()
+        # a read-only shared mapping with a read-only registration first; where that is refused, a writable shared
+        # mapping (never written to) with a plain registration
+        for mode, access, ro in (("rb", mmap.ACCESS_READ, 1), ("r+b", mmap.ACCESS_WRITE, 0)):
+            try:
+                with open(info.path, mode) as f:
+                    mm = mmap.mmap(f.fileno(), 0, access=access)
+            except (OSError, ValueError):
+                continue
+            arr = np.frombuffer(mm, dtype=np.uint8)
+            addr = arr.ctypes.data
+            del arr
+            if lib.bv_host_register(ctypes.c_void_p(addr), size, ro) == 0:
+                m = cls(info, mm, addr, size)
+                m.mode = "read-only mapping" if ro else "writable shared mapping"
+                return m
+            try:
+                mm.close()
+            except BufferError:
+                pass
+        return None
+
+    def planes(self, i: int, luma_only: bool = False):
+        inf = self.info
+        off = inf.header_bytes + i * (inf.frame_header_bytes + inf.frame_bytes) + inf.frame_header_bytes
+        if i < 0 or off + inf.frame_bytes > self._len:
+            raise EOFError(f"{inf.path}: frame {i} is past the end of the file")
+        out = []
+        bps = self._dtype.itemsize
+        for (h, w) in self._shapes[: 1 if luma_only else len(self._shapes)]:
+            n = h * w * bps
+            a = self._buf[off:off + n]
+            out.append(a.view(self._dtype).reshape(h, w))       # 16-bit planes may sit at odd addresses: the copy engine does not care
+            off += n
+        return out
+
+    def close(self):
+        if self._mm is None:
+            return
+        import ctypes
+        from . import _lib as L
+        L.load().bv_host_unregister(ctypes.c_void_p(self._addr))
+        self._buf = None
+        try:
+            self._mm.close()
+        except BufferError:            # a view is still alive somewhere; the mapping goes with it
+            pass
+        self._mm = None
+
+
 def write_y4m(path: str, frames, width: int, height: int, bpc: int = 8, fps=(30, 1), chroma: int = 420) -> None:
     """frames: iterable of [Y, U, V] arrays.  Header as ffmpeg expects."""
     tag = {(420, 8): "420jpeg", (422, 8): "422", (444, 8): "444", (400, 8): "mono"}.get((chroma, bpc))

@@ -110,6 +110,18 @@ def _fake_shard(src, model, opt, device, start, end, mask):
     return out
 
 
+class _FakeSession:
+    def __init__(self, rank):
+        self.rank = rank
+
+    def analyze(self, clip, model, opt):
+        if clip.nb_frames == 13:
+            raise RuntimeError("bad clip")
+        assert opt.devices == (self.rank,)
+        return {"pooled_metrics": {"vmaf": {"mean": float(clip.nb_frames)}}, "n_frames": clip.nb_frames,
+                "model": model.name, "rank": self.rank}
+
+
 def _worker(rank, world, port, n, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -120,10 +132,16 @@ def _worker(rank, world, port, n, q):
         opt = engine.EngineOptions(svr_on_device=False)
         res = D.analyze_distributed(_FakeClip(n), model, opt, shard_fn=_fake_shard)
         t = D.max_over_ranks(10.0 + rank)
+        # whole clips dealt over the ranks (configs[4]): summaries come back on rank 0 in input order, a failing clip
+        # fills its own slot only
+        clips = [_FakeClip(k) for k in (11, 12, 13, 14, 15)]
+        batch = D.analyze_batch_distributed(clips, model, opt, device=rank, session=_FakeSession(rank))
         if rank == 0:
+            assert [b.get("n_frames") for b in batch] == [11, 12, None, 14, 15] and "bad clip" in batch[2]["error"]
+            assert [b["rank"] for b in batch if "rank" in b] == [0, 1, 1, 0]
             q.put(([fr["metrics"] for fr in res["frames"]], res["pooled_metrics"]["vmaf"], t))
         else:
-            assert res is None and t == 10.0 + world - 1
+            assert res is None and batch is None and t == 10.0 + world - 1
     finally:
         dist.destroy_process_group()
 

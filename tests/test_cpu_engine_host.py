@@ -201,3 +201,24 @@ def test_failed_shard_stops_its_siblings_and_the_error_surfaces(fake, monkeypatc
     with pytest.raises(OSError):
         engine.analyze(Boom(4000), M.resolve_model("vmaf_v0.6.1"), _opt(devices=(0, 0)))
     assert max(len(fx.frames) for fx in fake.instances) < 2000           # the healthy shard did not run to its end
+
+
+def test_file_source_reader_threads_fill_the_ring_in_order(fake, tmp_path):
+    """Raw clips that cannot be mapped + registered (no GPU here; small files) go through the pinned ring filled by
+    several reader threads: every frame must reach the extractor exactly once, in order, with its own content."""
+    from pqa2_b200 import yuvio
+    w, h, n = 64, 48, 150
+    def frames(mul):
+        for i in range(n):
+            yield [np.full((h, w), (i * mul) % 251, np.uint8), np.full((h // 2, w // 2), 7, np.uint8),
+                   np.full((h // 2, w // 2), 9, np.uint8)]
+    rp, dp = str(tmp_path / "r.y4m"), str(tmp_path / "d.y4m")
+    yuvio.write_y4m(rp, frames(1), w, h)
+    yuvio.write_y4m(dp, frames(3), w, h)
+    src = engine.FileSource(yuvio.probe(rp), yuvio.probe(dp))
+    assert not src.zero_copy and src.parallel_reads
+    res = engine.analyze(src, M.resolve_model("vmaf_v0.6.1"), _opt(batch_frames=8, reader_threads=4, devices=(0, 0)))
+    src.release()
+    got = sorted((idx, content) for fx in fake.instances for idx, content, fl in fx.frames if not fl & L.FRAME_LEAD_IN)
+    assert got == [(i, i % 251) for i in range(n)]
+    assert [fr["frameNum"] for fr in res["frames"]] == list(range(n))
