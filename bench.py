@@ -416,10 +416,11 @@ def measure_workload(cx: Ctx, wname: str, wl: dict, pool: Pool, steps: int, warm
     bps = pool.bps
     fps_step = args.frames_per_step or wl["frames_per_step"]
     model = M.resolve_model(wl["model"])
-    opt = engine.EngineOptions(psnr=wl["psnr"], ssim=wl["ssim"], ms_ssim=wl["ms_ssim"], devices=(local,))
+    fast = bool(getattr(args, "fast_float", False)) and model.is_float
+    opt = engine.EngineOptions(psnr=wl["psnr"], ssim=wl["ssim"], ms_ssim=wl["ms_ssim"], devices=(local,), fast_float=fast)
     mask = engine.feature_mask(model, opt)
     fx = FeatureExtractor(w, h, bpc, 420 if pool.chroma else 0, mask, local, vif_enhn_gain_limit=model.vif_enhn_gain_limit,
-                          adm_enhn_gain_limit=model.adm_enhn_gain_limit)
+                          adm_enhn_gain_limit=model.adm_enhn_gain_limit, fast_float=fast)
     counter = [0]
     # bytes of one frame of one clip that the enabled features actually read (luma only unless psnr / ssim stats want chroma)
     uses_chroma = pool.chroma and bool(mask & (L.FEAT_PSNR_UV | L.FEAT_FFSSIM))
@@ -702,6 +703,7 @@ def main() -> int:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only (profiling runs)")
     ap.add_argument("--frames-per-step", type=int, default=0)
+    ap.add_argument("--fast-float", action="store_true", help="float workloads with bv_opts.fast_float (opt-in build)")
     ap.add_argument("--sharded-frames", type=int, default=SHARDED_FRAMES)
     ap.add_argument("--batch-clips", type=int, default=BATCH_CLIPS)
     args = ap.parse_args()

@@ -56,7 +56,11 @@ typedef struct bv_opts {
     double adm_norm_view_dist;       /* 3.0   */
     int    adm_ref_display_height;   /* 1080  */
     int    batch_frames;             /* frame pairs per kernel launch group (0 = auto) */
-    int    reserved[6];
+    int    fast_float;               /* float extractors only, opt-in: contract multiply-add and fold the symmetric filter
+                                        taps (half the FP32 work).  Results leave libvmaf's scalar operation order but stay
+                                        inside the float models' tolerance (measured: profiles/r02_fast_float.md).  0 =
+                                        faithful order (default). */
+    int    reserved[5];
 } bv_opts;
 
 #define BV_RAW_WORDS 64

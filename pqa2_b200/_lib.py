@@ -44,7 +44,7 @@ ERR_ARG, ERR_CUDA, ERR_CANCELLED, ERR_ORDER, ERR_UNSUPPORTED = -1, -2, -3, -4, -
 class BvOpts(C.Structure):
     _fields_ = [("vif_enhn_gain_limit", C.c_double), ("adm_enhn_gain_limit", C.c_double),
                 ("adm_norm_view_dist", C.c_double), ("adm_ref_display_height", C.c_int),
-                ("batch_frames", C.c_int), ("reserved", C.c_int * 6)]
+                ("batch_frames", C.c_int), ("fast_float", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class BvFrameFeatures(C.Structure):

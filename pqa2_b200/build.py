@@ -21,6 +21,8 @@ LIB = os.path.join(HERE, "libb200vmaf.so")
 # in the VIF variance / ADM threshold terms moves VMAF by ~1e-4, and float_ssim by ~1e-6).
 EXACT = ["bv_motion.cu", "bv_vif.cu", "bv_adm.cu", "bv_misc.cu", "bv_api.cu", "bv_model.cu", "bv_float.cu"]
 FAST = []
+# bv_float.cu a second time with -DBV_FAST_FLOAT (contracted multiply-add, folded symmetric taps): bv_opts.fast_float
+VARIANTS = {"bv_float_fast.o": ("bv_float.cu", ["-DBV_FAST_FLOAT"])}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off",
           "--expt-relaxed-constexpr"]
@@ -56,6 +58,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 flags += ["-Xptxas", "-v"]
             jobs.append([nvcc, *ARCH, *flags, "-c", src, "-o", obj])
 
+    for oname, (sname, extra) in VARIANTS.items():
+        src = os.path.join(CSRC, sname)
+        obj = os.path.join(BUILD, oname)
+        if force or _stale(obj, [src] + headers):
+            flags = list(COMMON) + ["--fmad=false"] + extra
+            if verbose:
+                flags += ["-Xptxas", "-v"]
+            jobs.append([nvcc, *ARCH, *flags, "-c", src, "-o", obj])
+
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -66,9 +77,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for out in ex.map(run, jobs):
             if verbose and out:
                 sys.stderr.write(out)
-    objs = [os.path.join(BUILD, n.replace(".cu", ".o")) for n in EXACT + FAST]
+    objs = [os.path.join(BUILD, n.replace(".cu", ".o")) for n in EXACT + FAST] + [os.path.join(BUILD, n) for n in VARIANTS]
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+        # the shared CUDA runtime (found through the rpath, or already loaded by torch under the same soname): the
+        # static one would embed its whole entry-point table in the shipped library
+        cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
+        run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "shared", "-Xlinker", f"-rpath={cuda_lib}",
+             "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-lpthread", "-ldl", "-lrt"])
     return LIB
 
 

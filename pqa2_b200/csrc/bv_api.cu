@@ -95,6 +95,7 @@ struct bv_ctx {
     int *d_div = nullptr;
     // float extractors
     BvFloatState *fl = nullptr;
+    BvFloatStateFast *flf = nullptr;    // opts.fast_float: the contracted / folded-tap build of the same kernels
 };
 
 namespace {
@@ -198,8 +199,9 @@ int alloc_ctx(bv_ctx *c)
         c->adm.div_lookup = c->d_div;
     }
     if (c->feat & (BV_FEAT_VMAF_FLOAT | BV_FEAT_FLOAT_SSIM | BV_FEAT_FLOAT_MS_SSIM)) {
-        c->fl = bv_float_create(c->w, c->h, c->bpc, c->feat, B, &c->opts);
-        if (!c->fl) return fail(c, BV_ERR_CUDA, "bv_float_create failed (out of device memory?)");
+        if (c->opts.fast_float) c->flf = bv_float_fast_create(c->w, c->h, c->bpc, c->feat, B, &c->opts);
+        else c->fl = bv_float_create(c->w, c->h, c->bpc, c->feat, B, &c->opts);
+        if (!c->fl && !c->flf) return fail(c, BV_ERR_CUDA, "bv_float_create failed (out of device memory?)");
     }
     return 0;
 }
@@ -295,6 +297,7 @@ void finish_frame(bv_ctx *c, const Group &g, int f, bv_frame_features &o)
         valid |= BV_FEAT_FFSSIM;
     }
     if (c->fl) valid |= bv_float_finish(c->fl, g.h_fraw + (size_t)f * BV_FRAW_WORDS, g.flags[f], &o);
+    if (c->flf) valid |= bv_float_fast_finish(c->flf, g.h_fraw + (size_t)f * BV_FRAW_WORDS, g.flags[f], &o);
     o.valid_mask = valid;
 }
 
@@ -384,6 +387,7 @@ int launch_group(bv_ctx *c, Group &g)
         }
     }
     if (c->fl) bv_float_launch(c->fl, b, ry, dy, g.d_fraw, L);
+    if (c->flf) bv_float_fast_launch(c->flf, b, ry, dy, g.d_fraw, L);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(g.h_raw, g.d_raw, sizeof(unsigned long long) * g.n * BV_RAW_WORDS, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(g.h_fraw, g.d_fraw, sizeof(double) * g.n * BV_FRAW_WORDS, cudaMemcpyDeviceToHost, st));
@@ -539,6 +543,7 @@ void bv_destroy(bv_ctx *c)
     if (c->feat & BV_FEAT_ADM) { for (int s = 0; s < 3; ++s) if (c->adm.bands[s]) cudaFree(c->adm.bands[s]); if (c->adm.rows) cudaFree(c->adm.rows); }
     if (c->d_div) cudaFree(c->d_div);
     if (c->fl) bv_float_destroy(c->fl);
+    if (c->flf) bv_float_fast_destroy(c->flf);
     for (int k = 0; k < 2; ++k) if (c->t_ev[k]) cudaEventDestroy(c->t_ev[k]);
     if (c->up) cudaStreamDestroy(c->up);
     if (c->comp) cudaStreamDestroy(c->comp);
@@ -651,6 +656,7 @@ int bv_reset(bv_ctx *c)
     c->ready.store(0);
     c->blur_prev_n = 0;
     if (c->fl) bv_float_reset(c->fl);
+    if (c->flf) bv_float_fast_reset(c->flf);
     return 0;
 }
 

@@ -39,7 +39,8 @@ class EngineOptions:
     batch_frames: int = 0
     svr_on_device: bool = True
     extra_features: int = 0          # extra _lib.FEAT_* bits
-    reader_threads: int = 4          # file readers per shard when clips cannot be mapped (pinned-ring path)
+    fast_float: bool = False         # float models only, opt-in: contracted / folded-tap stencils (bv_opts.fast_float)
+    reader_threads: int = 8          # file readers per shard when clips cannot be mapped (pinned-ring path)
     float_motion: bool = False       # `feature=name=motion` (app/vmaf_analyzer.py:388-402): libvmaf's float motion
                                      # extractor next to the model's own features -> `motion`, `motion2` in the log
 
@@ -272,12 +273,13 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
         # one context (and one pinned ring) per shard: two shards on the same GPU must never share a bv_ctx
         # (include/b200vmaf.h: one host thread per ctx)
         key = (device, shard, src.width, src.height, src.bpc, src.chroma if not luma_only else 0, mask,
-               model.vif_enhn_gain_limit, model.adm_enhn_gain_limit, opt.batch_frames)
+               model.vif_enhn_gain_limit, model.adm_enhn_gain_limit, opt.batch_frames, bool(opt.fast_float))
         fx = session._extractor(key) if session is not None else None
         if fx is None:
             fx = FeatureExtractor(src.width, src.height, src.bpc, src.chroma if not luma_only else 0, mask, device,
                                   vif_enhn_gain_limit=model.vif_enhn_gain_limit,
-                                  adm_enhn_gain_limit=model.adm_enhn_gain_limit, batch_frames=opt.batch_frames)
+                                  adm_enhn_gain_limit=model.adm_enhn_gain_limit, batch_frames=opt.batch_frames,
+                                  fast_float=opt.fast_float)
             if session is not None:
                 session._keep_extractor(key, fx)
         else:

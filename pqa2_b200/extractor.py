@@ -43,7 +43,7 @@ class FeatureExtractor:
     def __init__(self, width: int, height: int, bpc: int = 8, chroma: int = 420,
                  features: int = L.FEAT_VMAF_INT, device: int = 0, vif_enhn_gain_limit: float = 100.0,
                  adm_enhn_gain_limit: float = 100.0, adm_norm_view_dist: float = 3.0,
-                 adm_ref_display_height: int = 1080, batch_frames: int = 0):
+                 adm_ref_display_height: int = 1080, batch_frames: int = 0, fast_float: bool = False):
         self.lib = L.load()
         self.width, self.height, self.bpc, self.chroma = width, height, bpc, chroma
         self.features, self.device = features, device
@@ -53,6 +53,7 @@ class FeatureExtractor:
         o.adm_norm_view_dist = adm_norm_view_dist
         o.adm_ref_display_height = adm_ref_display_height
         o.batch_frames = batch_frames
+        o.fast_float = 1 if fast_float else 0
         self._ctx = self.lib.bv_create(device, width, height, bpc, chroma, features, C.byref(o))
         if not self._ctx:
             raise BvError(L.ERR_CUDA, (self.lib.bv_last_error(None) or b"bv_create failed").decode())

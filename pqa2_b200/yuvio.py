@@ -257,7 +257,7 @@ class MappedClip:
 
     def __init__(self, info: ClipInfo, mm, base_addr: int, registered_len: int):
         self.info, self._mm, self._addr, self._len = info, mm, base_addr, registered_len
-        self._dtype = np.uint8 if info.bpc == 8 else np.dtype("<u2")
+        self._dtype = np.dtype(np.uint8) if info.bpc == 8 else np.dtype("<u2")
         self._buf = np.frombuffer(mm, dtype=np.uint8)
         self._shapes = info.plane_shapes()
 
