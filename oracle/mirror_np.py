@@ -1,0 +1,269 @@
+"""Independent NumPy mirror of the integer VIF / integer motion / float VIF arithmetic -- TEST INFRASTRUCTURE.
+
+A second restatement of libvmaf's published algorithm (integer_vif.c, integer_motion.c, vif.c / vif_tools.c; reached
+from the reference at app/vmaf_analyzer.py:417), written separately from
+oracle/vmaf_oracle.c: whole-plane array operations instead of per-pixel loops, Python integers / float64 where libvmaf
+uses 64-bit or double.  tests/test_oracle_mirror.py checks the C oracle against it accumulator for accumulator, so a
+slip in one of the two shows up.  PARITY UNPINNED all the same: both restate the same third-party source from
+memory; only a libvmaf log (tests/golden/libvmaf/) pins either.
+
+Only tests/ may import this module."""
+from __future__ import annotations
+
+import numpy as np
+
+VIF_TAPS = [
+    [489, 935, 1640, 2640, 3896, 5274, 6547, 7455, 7784, 7455, 6547, 5274, 3896, 2640, 1640, 935, 489],
+    [1244, 3663, 7925, 12590, 14692, 12590, 7925, 3663, 1244],
+    [3571, 16004, 26386, 16004, 3571],
+    [10904, 43728, 10904],
+]
+MOTION_TAPS = [3571, 16004, 26386, 16004, 3571]
+
+
+def _pad_reflect101(a: np.ndarray, r: int, axis: int) -> np.ndarray:
+    """integer_vif.c pads by reflection WITHOUT repeating the edge sample: index -i <- i, n-1+i <- n-1-i."""
+    return np.pad(a, [(r, r) if k == axis else (0, 0) for k in range(a.ndim)], mode="reflect")
+
+
+def _pad_mirror(a: np.ndarray, r: int, axis: int) -> np.ndarray:
+    """integer_motion.c / the float convolutions: -i <- i at the top/left, n-1+i <- n-i at the bottom/right
+    (index >= n maps to 2n - i - 1, i.e. the edge sample IS repeated there)."""
+    n = a.shape[axis]
+    idx = np.arange(-r, n + r)
+    idx = np.where(idx < 0, -idx, idx)
+    idx = np.where(idx >= n, 2 * n - idx - 1, idx)
+    return np.take(a, idx, axis=axis)
+
+
+def _fir(a: np.ndarray, taps, axis: int, pad) -> np.ndarray:
+    """sum_k taps[k] * a[i - r + k] along `axis` (object-free: int64 / uint64 is wide enough for every caller)."""
+    r = len(taps) // 2
+    p = pad(a, r, axis)
+    n = a.shape[axis]
+    out = np.zeros_like(a)
+    for k, t in enumerate(taps):
+        sl = [slice(None)] * a.ndim
+        sl[axis] = slice(k, k + n)
+        out = out + p[tuple(sl)] * t
+    return out
+
+
+def _log2_table() -> np.ndarray:
+    t = np.zeros(65536, np.int64)
+    i = np.arange(32767, 65536)
+    # C round(): ties away from zero (log2f(i) * 2048 lands exactly on .5 for 39 entries; round-half-even would differ there)
+    v = np.log2(i.astype(np.float64)).astype(np.float32).astype(np.float64) * 2048.0
+    t[32767:] = np.floor(v + 0.5).astype(np.int64)
+    return t
+
+
+_LOG2 = None
+
+
+def _best16_from32(v: np.ndarray):
+    """top 16 bits of a 32-bit value and the (negative) shift that produced them"""
+    v = v.astype(np.int64)
+    nbits = np.floor(np.log2(np.maximum(v, 1).astype(np.float64))).astype(np.int64) + 1      # bit length (exact below 2^53)
+    k = nbits - 16                                   # = 16 - clz32(v)
+    out = np.where(k >= 0, v >> np.maximum(k, 0), v << np.maximum(-k, 0))
+    return out, -k
+
+
+def _bitlen64(v) -> int:
+    return int(v).bit_length()
+
+
+def _best16_from64(values):
+    """libvmaf get_best16_from64 on Python integers (general form, all three branches)."""
+    outs, xs = [], []
+    for v in values:
+        v = int(v)
+        k = 64 - v.bit_length()                      # clz64
+        if k > 48:
+            sh = k - 48
+            outs.append((v << sh) & 0xFFFF); xs.append(sh)
+        elif k < 47:
+            sh = 48 - k
+            outs.append((v >> sh) & 0xFFFF); xs.append(-sh)
+        else:
+            x = 0
+            if v >> 16:
+                v >>= 1
+                x = -1
+            outs.append(v & 0xFFFF); xs.append(x)
+    return np.array(outs, np.int64), np.array(xs, np.int64)
+
+
+def vif_int(ref: np.ndarray, dis: np.ndarray, bpc: int = 8, egl: float = 100.0) -> np.ndarray:
+    """-> int64 [4, 7]: num_log, den_log, num_non_log, den_non_log, accum_x, accum_x2, count (= num_accum_x)
+    per scale, the accumulators of integer_vif.c's vif_statistic_8/16 (layout of oracle.vif()['acc'])."""
+    global _LOG2
+    if _LOG2 is None:
+        _LOG2 = _log2_table()
+    x = ref.astype(np.int64)
+    y = dis.astype(np.int64)
+    acc = np.zeros((4, 7), np.int64)
+    for scale in range(4):
+        taps = VIF_TAPS[scale]
+        if scale == 0:
+            sh, rnd = bpc, 1 << (bpc - 1)
+            sh_sq = 2 * (bpc - 8)
+            rnd_sq = 0 if bpc == 8 else 1 << (sh_sq - 1)
+        else:
+            # subsample: THIS scale's taps on the previous level (vertical rounding as that level's statistic), keep even samples
+            psh, prnd = (bpc, 1 << (bpc - 1)) if scale == 1 else (16, 32768)
+            lv = []
+            for p in (x, y):
+                v = (_fir(p, taps, 0, _pad_reflect101) + prnd) >> psh
+                hh = (_fir(v, taps, 1, _pad_reflect101) + 32768) >> 16
+                lv.append(hh[: (p.shape[0] // 2) * 2: 2, : (p.shape[1] // 2) * 2: 2])
+            x, y = lv
+            sh, rnd, sh_sq, rnd_sq = 16, 32768, 16, 32768
+        # vertical pass
+        mu1 = (_fir(x, taps, 0, _pad_reflect101) + rnd) >> sh
+        mu2 = (_fir(y, taps, 0, _pad_reflect101) + rnd) >> sh
+        xx = (_fir(x * x, taps, 0, _pad_reflect101) + rnd_sq) >> sh_sq
+        yy = (_fir(y * y, taps, 0, _pad_reflect101) + rnd_sq) >> sh_sq
+        xy = (_fir(x * y, taps, 0, _pad_reflect101) + rnd_sq) >> sh_sq
+        # horizontal pass: mu unshifted (u32), second moments (acc + 32768) >> 16
+        mu1 = _fir(mu1, taps, 1, _pad_reflect101)
+        mu2 = _fir(mu2, taps, 1, _pad_reflect101)
+        xx = (_fir(xx, taps, 1, _pad_reflect101) + 32768) >> 16
+        yy = (_fir(yy, taps, 1, _pad_reflect101) + 32768) >> 16
+        xy = (_fir(xy, taps, 1, _pad_reflect101) + 32768) >> 16
+        assert mu1.max() < 2 ** 32 and xx.max() < 2 ** 32
+        # Python-int products for the three (a*b + 2^31) >> 32 terms: up to 2^64
+        def mulhi_round(a, b):
+            return ((a.astype(object) * b.astype(object) + 2147483648) >> 32).astype(np.int64)
+        s1 = (xx - mulhi_round(mu1, mu1))
+        s2 = np.maximum(yy - mulhi_round(mu2, mu2), 0)
+        s12 = (xy - mulhi_round(mu1, mu2))
+        # the C code keeps these in int32: wrap like it does
+        s1 = ((s1 + 2 ** 31) % 2 ** 32) - 2 ** 31
+        s12 = ((s12 + 2 ** 31) % 2 ** 32) - 2 ** 31
+        nsq = 2 * 65536
+        lg = s1 >= nsq
+        d16, dx = _best16_from32((s1[lg] + nsq))
+        acc[scale, 1] = int(_LOG2[d16].sum())
+        acc[scale, 4] = int(dx.sum())
+        acc[scale, 6] = int(lg.sum())
+        gp = lg & (s12 > 0) & (s2 > 0)
+        g = s12[gp].astype(np.float64) / (s1[gp].astype(np.float64) + 65536 * 1.0e-10)
+        sv = np.trunc(s2[gp].astype(np.float64) - g * s12[gp].astype(np.float64)).astype(np.int64)
+        sv = ((sv + 2 ** 31) % 2 ** 32) - 2 ** 31            # (int32_t) conversion of an in-range double
+        sv = np.maximum(sv, 0)
+        g = np.minimum(g, egl)
+        n1 = sv + nsq
+        n2 = np.trunc(g * g * s1[gp].astype(np.float64)).astype(np.int64) + n1
+        t2, x1 = _best16_from64(n2)
+        t1, x2 = _best16_from64(n1)
+        acc[scale, 0] = int((_LOG2[t2] - _LOG2[t1]).sum())
+        acc[scale, 5] = int((x2 - x1).sum())
+        acc[scale, 2] = int(s2[~lg].sum())
+        acc[scale, 3] = int((~lg).sum())
+    return acc
+
+
+def vif_scores(acc: np.ndarray) -> np.ndarray:
+    """per-scale num / den as integer_vif.c finishes them (float num, den)."""
+    out = np.zeros(4)
+    for s in range(4):
+        a = [int(v) for v in acc[s]]
+        num = np.float32(a[0] / 2048.0 + a[5] + (a[3] - (a[2] / 16384.0) / 65025.0))
+        den = np.float32(a[1] / 2048.0 - (a[4] + a[6] * 17) + a[3])
+        out[s] = float(num / den)
+    return out
+
+
+def motion_blur_int(luma: np.ndarray, bpc: int = 8) -> np.ndarray:
+    p = luma.astype(np.int64)
+    v = (_fir(p, MOTION_TAPS, 0, _pad_mirror) + (1 << (bpc - 1))) >> bpc
+    return ((_fir(v, MOTION_TAPS, 1, _pad_mirror) + 32768) >> 16).astype(np.uint16)
+
+
+def motion_sad_int(a: np.ndarray, b: np.ndarray) -> int:
+    return int(np.abs(a.astype(np.int64) - b.astype(np.int64)).sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# float VIF with libvmaf's accumulation types: fp32 everywhere, per-row fp32 sums, rows added in double
+# ---------------------------------------------------------------------------------------------
+def _gauss(n: int) -> np.ndarray:
+    """vif kernels: normalised Gaussian, sigma = n / 5, evaluated in double and rounded to float (vif_options.h tables)"""
+    k = np.arange(n) - n // 2
+    g = np.exp(-(k.astype(np.float64) ** 2) / (2.0 * (n / 5.0) ** 2))
+    return (g / g.sum()).astype(np.float32)
+
+
+def _fir_f32(a: np.ndarray, taps: np.ndarray, axis: int) -> np.ndarray:
+    """libvmaf's scalar convolution order: acc = 0; acc += f[k] * v[k] left to right, every operation rounded to fp32"""
+    r = len(taps) // 2
+    p = _pad_mirror(a, r, axis)
+    n = a.shape[axis]
+    out = np.zeros(a.shape, np.float32)
+    for k, t in enumerate(taps):
+        sl = [slice(None)] * a.ndim
+        sl[axis] = slice(k, k + n)
+        out = (out + (p[tuple(sl)] * np.float32(t)).astype(np.float32)).astype(np.float32)
+    return out
+
+
+def _log2f_approx(x: np.ndarray) -> np.ndarray:
+    """vif_tools.c log2f_approx: exponent + degree-8 polynomial of the mantissa (Horner, fp32)"""
+    u = x.astype(np.float32).view(np.uint32)
+    e = ((u >> 23) & 0xFF).astype(np.int32) - 127
+    m = ((u & 0x007FFFFF) | 0x3F800000).view(np.float32) - np.float32(1.0)
+    c = [-0.012671635276421, 0.064841182402670, -0.157048836463065, 0.257167726303123, -0.353800560300520,
+         0.480131410397451, -0.721314327952201, 1.442694803896991, 0.0]
+    v = np.zeros(x.shape, np.float32)
+    for ck in c:
+        v = ((v * m).astype(np.float32) + np.float32(ck)).astype(np.float32)
+    return (e.astype(np.float32) + v).astype(np.float32)
+
+
+def vif_float(ref_f: np.ndarray, dis_f: np.ndarray, egl: float = 100.0, row_acc=np.float32, taps_of=None):
+    """-> (num[4], den[4]) doubles.  ref_f / dis_f: float32 luma - 128.  `row_acc` is the type of the per-row sums:
+    np.float32 is libvmaf's vif_statistic_s (float accum_num / accum_den per row, rows added into double);
+    np.float64 reproduces oracle/vmaf_float_oracle.c, which sums every pixel into double."""
+    x, y = ref_f.astype(np.float32), dis_f.astype(np.float32)
+    num, den = np.zeros(4), np.zeros(4)
+    f32 = np.float32
+    for scale in range(4):
+        taps = taps_of(scale) if taps_of else _gauss([17, 9, 5, 3][scale])      # literal tables when the caller has them
+        if scale > 0:
+            x = _fir_f32(_fir_f32(x, taps, 0), taps, 1)[: (x.shape[0] // 2) * 2: 2, : (x.shape[1] // 2) * 2: 2]
+            y = _fir_f32(_fir_f32(y, taps, 0), taps, 1)[: (y.shape[0] // 2) * 2: 2, : (y.shape[1] // 2) * 2: 2]
+        F = lambda p: _fir_f32(_fir_f32(p, taps, 0), taps, 1)
+        mu1, mu2 = F(x), F(y)
+        xx, yy, xy = F((x * x).astype(f32)), F((y * y).astype(f32)), F((x * y).astype(f32))
+        s1 = np.maximum((xx - (mu1 * mu1).astype(f32)).astype(f32), f32(0))
+        s2 = np.maximum((yy - (mu2 * mu2).astype(f32)).astype(f32), f32(0))
+        s12 = (xy - (mu1 * mu2).astype(f32)).astype(f32)
+        eps, nsq = f32(1.0e-10), f32(2.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            g = (s12 / (s1 + eps).astype(f32)).astype(f32)
+            sv = (s2 - (g * s12).astype(f32)).astype(f32)
+            c1 = s1 < eps
+            g = np.where(c1, f32(0), g); sv = np.where(c1, s2, sv)
+            c2 = s2 < eps
+            g = np.where(c2, f32(0), g); sv = np.where(c2, f32(0), sv)
+            c3 = g < 0
+            sv = np.where(c3, s2, sv); g = np.where(c3, f32(0), g)
+            sv = np.maximum(sv, eps)
+            g = np.minimum(g, f32(egl))
+            s1z = np.where(c1, f32(0), s1)
+            nv = _log2f_approx((f32(1) + (((g * g).astype(f32) * s1z).astype(f32) / (sv + nsq).astype(f32)).astype(f32)).astype(f32))
+            dv = _log2f_approx((f32(1) + (s1z / nsq).astype(f32)).astype(f32))
+        nv = np.where(s12 < 0, f32(0), nv)
+        flat = s1z < nsq
+        nv = np.where(flat, (f32(1) - (s2 * f32(4.0 / (255.0 * 255.0))).astype(f32)).astype(f32), nv).astype(f32)
+        dv = np.where(flat, f32(1), dv).astype(f32)
+        if row_acc is np.float32:
+            # sequential fp32 sum along each row (cumsum is left to right), rows added in double
+            num[scale] = float(np.cumsum(nv, axis=1, dtype=np.float32)[:, -1].astype(np.float64).sum())
+            den[scale] = float(np.cumsum(dv, axis=1, dtype=np.float32)[:, -1].astype(np.float64).sum())
+        else:
+            num[scale] = float(nv.astype(np.float64).sum())
+            den[scale] = float(dv.astype(np.float64).sum())
+    return num, den
