@@ -24,7 +24,9 @@ FAST = []
 # bv_float.cu a second time with -DBV_FAST_FLOAT (contracted multiply-add, folded symmetric taps): bv_opts.fast_float
 VARIANTS = {"bv_float_fast.o": ("bv_float.cu", ["-DBV_FAST_FLOAT"])}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off",
+# experiments: extra nvcc flags for every source, e.g. BV_EXTRA_NVCC_FLAGS="-DBV_VIF_STAT_FLAT" python -m pqa2_b200.build --force
+EXTRA = os.environ.get("BV_EXTRA_NVCC_FLAGS", "").split()
+COMMON = EXTRA + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off",
           "--expt-relaxed-constexpr"]
 
 

@@ -32,8 +32,9 @@ def _default_shard_fn(src, model, opt, device, start, end, mask, session=None):
 
 
 def _world(group=None):
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
+    import sys
+    dist = sys.modules.get("torch.distributed")       # never import torch here: a process group can only exist if the
+    if dist is not None and dist.is_available() and dist.is_initialized():      # caller already did (and the import costs seconds)
         return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
 
