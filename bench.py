@@ -70,7 +70,8 @@ def kernel_bytes(name: str, w: int, h: int, bps: int) -> float | None:
         # SAD of consecutive blurred frames: every blur plane of the group is needed once (frame i is "current" for
         # pair i and "previous" for pair i+1 of the same launch; the second use hits L2 -- ncu: DRAM reads = 1 plane/frame)
         "motion_sad": px * 2,
-        "vif_stat_s0": 2 * px * bps, "vif_subsample_s1": 2 * px * bps + 2 * lv[1] * 2,
+        # scale 0 also writes pyramid level 1 and the motion feature's blurred reference (fused consumers of the raw luma)
+        "vif_stat_s0": 2 * px * bps + 2 * lv[1] * 2 + px * 2, "vif_subsample_s1": 2 * px * bps + 2 * lv[1] * 2,
         "vif_stat_s1": 2 * lv[1] * 2, "vif_subsample_s2": 2 * lv[1] * 2 + 2 * lv[2] * 2,
         "vif_stat_s2": 2 * lv[2] * 2, "vif_subsample_s3": 2 * lv[2] * 2 + 2 * lv[3] * 2,
         "vif_stat_s3": 2 * lv[3] * 2,
@@ -553,14 +554,20 @@ def measure_sharded_4k(cx: Ctx, pool: Pool) -> dict:
     opt = engine.EngineOptions(devices=(cx.local,))
     n = cx.args.sharded_frames
     clip = pool.clip(n)
-    times, res = [], None
+    times, shard_s, res = [], [], None
     with engine.Engine() as sess:
+        def timed_shard(src, model_, opt_, device, start, end, mask):      # this rank's chunk: H2D + kernels + row read-back
+            t0 = time.perf_counter()
+            out = D._default_shard_fn(src, model_, opt_, device, start, end, mask, sess)
+            shard_s.append(time.perf_counter() - t0)
+            return out
+
         D.analyze_distributed(pool.clip(min(n, 64 * cx.world)), model, opt, device=cx.local, session=sess,
                               svr_device=cx.local)                 # warm-up: contexts, first launches
-        for _ in range(2):
+        for _ in range(3):
             cx.barrier()
             t0 = time.perf_counter()
-            r = D.analyze_distributed(clip, model, opt, device=cx.local, session=sess, svr_device=cx.local)
+            r = D.analyze_distributed(clip, model, opt, device=cx.local, shard_fn=timed_shard, svr_device=cx.local)
             dt = time.perf_counter() - t0            # rank 0 returns after the gather, the SVR and the pooling
             times.append(cx.max_over_ranks(dt))
             res = r if r is not None else res
@@ -569,7 +576,7 @@ def measure_sharded_4k(cx: Ctx, pool: Pool) -> dict:
             dt = min(times)
             per_frame = 2 * pool.frame_bytes
             rec = {"value": n / dt, "unit": "frames/s", "frames": n, "n_gpus": cx.world, "scaling": "strong",
-                   "seconds": dt, "runs": [round(t, 4) for t in times],
+                   "seconds": dt, "runs": [round(t, 4) for t in times], "rank0_shard_seconds": [round(t, 4) for t in shard_s],
                    "workload": f"configs[2]: ONE 3840x2160 yuv420p10le clip of {n} frames (a pinned pool of {pool.P} distinct "
                                f"frame pairs, cycled), {wl['model']}, contiguous frame chunks + one-frame lead-in per rank, "
                                "rows gathered on rank 0",
@@ -738,7 +745,7 @@ def main() -> int:
 
     # ---- headline workload
     t0 = time.perf_counter()
-    pool = Pool(wl["w"], wl["h"], wl["bpc"], wl["pool"], 100 + rank, wl["psnr"], local)
+    pool = Pool(wl["w"], wl["h"], wl["bpc"], wl["pool"], 100, wl["psnr"], local)      # the same clip on every rank
     if rank == 0:
         log(f"[bench] synthesised {wl['pool']} frame pairs {wl['w']}x{wl['h']} {wl['bpc']}-bit in {time.perf_counter() - t0:.1f}s")
     head = measure_workload(cx, wname, wl, pool, args.steps, args.warmup, True, not args.no_e2e)

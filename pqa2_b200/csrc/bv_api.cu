@@ -23,6 +23,8 @@
 #include <string>
 #include <vector>
 
+int bv_vif_fuse_mask();         // bv_vif.cu
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -357,17 +359,22 @@ int launch_group(bv_ctx *c, Group &g)
     g.prof.on = c->profiling;
     const BvLaunch L = { st, &g.prof, &c->nlaunch };
 
-    if (c->feat & BV_FEAT_MOTION) {
-        uint16_t *cur = c->blur[c->blur_cur];
-        const uint16_t *prev_last = c->blur_prev_n > 0
-            ? c->blur[c->blur_cur ^ 1] + (size_t)(c->blur_prev_n - 1) * c->blur_elems : cur;
-        bv_launch_motion_blur(b, ry, c->bpc, c->w, c->h, cur, c->blur_elems, L);
-        bv_launch_motion_sad(b, cur, prev_last, c->blur_elems, c->w, c->h, g.d_raw, L);
-        c->blur_prev_n = g.n;
-        c->blur_cur ^= 1;
+    {
+        // integer motion + VIF: with both enabled the blur rides on the VIF scale-0 kernel's staged tile; the SAD follows
+        uint16_t *cur = (c->feat & BV_FEAT_MOTION) ? c->blur[c->blur_cur] : nullptr;
+        const bool fused_blur = cur && (c->feat & BV_FEAT_VIF) && (bv_vif_fuse_mask() & 2);
+        if (cur && !fused_blur) bv_launch_motion_blur(b, ry, c->bpc, c->w, c->h, cur, c->blur_elems, L);
+        if (c->feat & BV_FEAT_VIF)
+            bv_launch_vif(b, ry, dy, c->bpc, c->vif_lv, c->d_log2, c->d_log2c, c->opts.vif_enhn_gain_limit, g.d_raw, L,
+                          fused_blur ? cur : nullptr, c->blur_elems);
+        if (cur) {
+            const uint16_t *prev_last = c->blur_prev_n > 0
+                ? c->blur[c->blur_cur ^ 1] + (size_t)(c->blur_prev_n - 1) * c->blur_elems : cur;
+            bv_launch_motion_sad(b, cur, prev_last, c->blur_elems, c->w, c->h, g.d_raw, L);
+            c->blur_prev_n = g.n;
+            c->blur_cur ^= 1;
+        }
     }
-    if (c->feat & BV_FEAT_VIF)
-        bv_launch_vif(b, ry, dy, c->bpc, c->vif_lv, c->d_log2, c->d_log2c, c->opts.vif_enhn_gain_limit, g.d_raw, L);
     if (c->feat & BV_FEAT_ADM) {
         CK(cudaMemsetAsync(c->adm.rows, 0, sizeof(unsigned long long) * c->adm.rows_frame_stride * g.n, st));
         bv_launch_adm(b, ry, dy, c->bpc, c->adm, c->adm_sp, c->opts.adm_enhn_gain_limit, g.d_raw, L);

@@ -307,9 +307,11 @@ struct BvVifLevels {                        // u16 pyramid levels 1..3 (tight pi
     int w[4], h[4];
 };
 #define BV_LOG2C_BYTES (1024 + 16384)       // 512 u16 bases + 32768 4-bit deltas
+// motion_blur_out != nullptr: the scale-0 kernel also writes the integer motion feature's blurred reference (for every
+// frame of the group, scored or not), so the caller skips bv_launch_motion_blur.
 void bv_launch_vif(const BvBatch &b, BvPlane ref_y, BvPlane dis_y, int bpc, const BvVifLevels &lv,
                    const uint16_t *log2_table, const uint8_t *log2_packed, double egl, unsigned long long *raw,
-                   const BvLaunch &L);
+                   const BvLaunch &L, uint16_t *motion_blur_out = nullptr, size_t motion_blur_frame_elems = 0);
 // adm
 struct BvAdmBuffers {
     void *bands[4];                         // scale s: [frame][ref/dis][a,v,h,d][h][w], i16 (s=0) / i32

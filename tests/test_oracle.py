@@ -141,3 +141,14 @@ def test_synthetic_frames_exercise_every_branch():
     assert aneg["adm2"] < a["adm2"], "the ADM gain limit only acts where the angle flag is set"
     same = oracle.adm(ref, ref, 8, 1.0)
     assert abs(same["adm2"] - 1.0) < 1e-4
+
+
+def test_oracle_matches_fullsize_golden_1080p():
+    """tests/golden/fullsize_oracle.json (1080p 8-bit case; the 2160p cases are checked against the kernels by the -m gpu
+    suite, the scalar oracle needs several seconds for each of them)."""
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fullsize_oracle.json")))
+    c = next(c for c in g["cases"] if c["w"] == 1920)
+    rp, dp = synth.frame_pair(c["seed"], 0, c["w"], c["h"], c["bpc"], chroma=False)
+    v, a = oracle.vif(rp[0], dp[0], c["bpc"], c["egl"]), oracle.adm(rp[0], dp[0], c["bpc"], c["egl"])
+    assert v["acc"].tolist() == c["vif_acc"] and a["cm"].tolist() == c["adm_cm"] and a["adm2"] == c["adm2"]
+    assert [[int(x) for x in r] for r in a["den"]] == c["adm_den"] and oracle.sse(rp[0], dp[0], c["bpc"]) == c["sse_y"]

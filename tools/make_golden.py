@@ -50,5 +50,21 @@ def main():
         print(path)
 
 
+def fullsize():
+    """One frame pair at each BASELINE picture size: raw integer accumulators only (the float rows would take minutes)."""
+    cases = []
+    for seed, w, h, bpc, egl in ((11, 1920, 1080, 8, 100.0), (12, 3840, 2160, 10, 100.0), (12, 3840, 2160, 10, 1.0)):
+        rp, dp = synth.frame_pair(seed, 0, w, h, bpc, chroma=False)
+        v, a = oracle.vif(rp[0], dp[0], bpc, egl), oracle.adm(rp[0], dp[0], bpc, egl)
+        cases.append({"seed": seed, "w": w, "h": h, "bpc": bpc, "egl": egl, "vif_acc": v["acc"].tolist(),
+                      "adm_cm": a["cm"].tolist(), "adm_den": [[int(x) for x in r] for r in a["den"]], "adm2": a["adm2"],
+                      "sse_y": int(oracle.sse(rp[0], dp[0], bpc))})
+    path = os.path.join(ROOT, "tests", "golden", "fullsize_oracle.json")
+    with open(path, "w") as f:
+        json.dump({"source": "oracle/ (CPU restatement; not reference output)", "cases": cases}, f, indent=1)
+    print(path)
+
+
 if __name__ == "__main__":
     main()
+    fullsize()
