@@ -672,7 +672,7 @@ def measure_file_e2e(cx: Ctx, pool: Pool) -> dict:
             if res is None:
                 return {"value": None, "note": "analyze_videos failed: " + "; ".join(errs)}
         ingest = "mmap + cudaHostRegister (page cache -> GPU, no CPU copy)" if getattr(a, "last_ingest", "") == "mapped" \
-            else "reader threads -> pinned ring"
+            else "reader threads (auto: 12 on a 16-core host) -> pinned ring -> cudaMemcpyAsync"
         return {"value": n / min(runs[1:]), "unit": "frames/s", "frames": n, "first_call_fps": n / runs[0],
                 "runs_s": [round(t, 4) for t in runs], "ingest": ingest, "clip_dir": base,
                 "bytes_read_per_call": int(2 * n * pool.frame_bytes),

@@ -40,7 +40,7 @@ class EngineOptions:
     svr_on_device: bool = True
     extra_features: int = 0          # extra _lib.FEAT_* bits
     fast_float: bool = False         # float models only, opt-in: contracted / folded-tap stencils (bv_opts.fast_float)
-    reader_threads: int = 8          # file readers per shard when clips cannot be mapped (pinned-ring path)
+    reader_threads: int = 0          # file readers per shard (pinned-ring path); 0 = auto (cores / shards, 2 .. 16)
     float_motion: bool = False       # `feature=name=motion` (app/vmaf_analyzer.py:388-402): libvmaf's float motion
                                      # extractor next to the model's own features -> `motion`, `motion2` in the log
 
@@ -65,12 +65,14 @@ class FrameSource:
 
 
 class FileSource(FrameSource):
-    """A reference / distorted pair of clip files.  Raw clips (.y4m / planar .yuv) are mapped and registered with
-    CUDA when the platform allows it (``yuvio.MappedClip``): the shards then hand page-cache views straight to
-    ``bv_submit`` (``zero_copy``).  Otherwise -- and for containers -- frames are read into a pinned ring by
-    reader threads (``_Prefetcher``)."""
+    """A reference / distorted pair of clip files.  Frames are read into a pinned ring by reader threads
+    (``_Prefetcher``: 12 threads deliver ~36 GB/s from the page cache on the B200 box).  ``mapped=True`` instead maps raw
+    clips (.y4m / planar .yuv) and registers the mapping with CUDA (``yuvio.MappedClip``), so the shards hand page-cache
+    views straight to ``bv_submit`` with no CPU copy (39 GB/s, PCIe-bound) -- but cudaHostRegister pins pages at only
+    ~6 GB/s (0.3 s for a 1.9 GB pair; tmpfs only, ext4 / overlay mappings are refused), so it pays off only for a source
+    that is analysed several times (several models over one clip pair); it is opt-in."""
 
-    def __init__(self, ref_info, dis_info, mapped: bool | None = None):
+    def __init__(self, ref_info, dis_info, mapped: bool = False):
         from .yuvio import ClipReader
         self._ri, self._di = ref_info, dis_info
         self.width, self.height, self.bpc, self.chroma = ref_info.width, ref_info.height, ref_info.bpc, ref_info.chroma
@@ -88,7 +90,7 @@ class FileSource(FrameSource):
         with self._lock:
             if self._maps is None:
                 self._maps = False
-                if self._want_mapped is not False and not self.sequential:
+                if self._want_mapped and not self.sequential:
                     from .yuvio import MappedClip
                     r = MappedClip.open(self._ri)
                     d = MappedClip.open(self._di) if r is not None else None
@@ -220,6 +222,23 @@ class SynthSource(FrameSource):
             dis_planes[k][...] = dp[k]
 
 
+class PlaneList(list):
+    """[Y, U, V] views of ONE pinned buffer (``flat``, uint8): a reader can fill a whole frame with a single read."""
+    flat = None
+
+
+def pinned_planes(shapes, dtype) -> PlaneList:
+    item = np.dtype(dtype).itemsize
+    sizes = [int(np.prod(s)) * item for s in shapes]
+    flat = pinned_empty((sum(sizes),), np.uint8)
+    out, off = PlaneList(), 0
+    for s, n in zip(shapes, sizes):
+        out.append(flat[off:off + n].view(dtype).reshape(s))
+        off += n
+    out.flat = flat
+    return out
+
+
 def _plane_shapes(src: FrameSource):
     w, h = src.width, src.height
     if src.chroma in (0, 400):
@@ -290,13 +309,19 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
         ring = None
         if not zero_copy:
             ring = session._ring(key, shapes, dtype, 2 * B) if session is not None else \
-                [([pinned_empty(s, dtype) for s in shapes], [pinned_empty(s, dtype) for s in shapes]) for _ in range(2 * B)]
+                [(pinned_planes(shapes, dtype), pinned_planes(shapes, dtype)) for _ in range(2 * B)]
         lead = (1 if start > 0 else 0) if lead_in is None else (1 if lead_in and start > 0 else 0)
         ordinal = 0
         ids = list(range(start - lead, end))
         if not zero_copy:
             # raw files: several readers (page-cache copies run beside each other); a decoder is one sequential stream
-            n_readers = opt.reader_threads if getattr(src, "parallel_reads", False) else 1
+            n_readers = 1
+            if getattr(src, "parallel_reads", False):
+                import os
+                # auto: three quarters of the host's cores shared out over the shards, 2 .. 12 readers each.  One reader
+                # copies ~4 GB/s out of the page cache; measured on the 16-core B200 box (tools/ingest_probe.py): 4 / 8 /
+                # 12 / 16 readers deliver 21 / 32 / 36 / 26 GB/s -- past 12 they fight the submitting thread for cores
+                n_readers = opt.reader_threads or max(2, min(12, ((os.cpu_count() or 4) * 3 // 4) // max(1, len(opt.devices))))
             pre = _Prefetcher(src, handle, ring, ids, luma_only, n_readers)
         # pictures large enough for a reduced group size are upload-bound over PCIe: only there does a short last
         # launch shorten the call; at <= 1440p the GPU is the bottleneck and short groups would only run less efficiently
@@ -379,8 +404,7 @@ class Engine:
         with self._lock:
             r = self._rings.get(key)
             if r is None:
-                r = self._rings[key] = [([pinned_empty(s, dtype) for s in shapes], [pinned_empty(s, dtype) for s in shapes])
-                                        for _ in range(n)]
+                r = self._rings[key] = [(pinned_planes(shapes, dtype), pinned_planes(shapes, dtype)) for _ in range(n)]
             return r
 
     def analyze(self, src, model, opt=None, progress_cb=None, cancel=None, frame_range=None):

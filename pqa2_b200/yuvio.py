@@ -239,6 +239,14 @@ class ClipReader:
         return [np.empty(s, self._dtype) for s in self.info.plane_shapes()]
 
     def read_into(self, i: int, planes, luma_only: bool = False) -> None:
+        flat = getattr(planes, "flat", None)
+        if flat is not None and not luma_only and len(planes) == len(self.info.plane_shapes()) and \
+                flat.nbytes == self.info.frame_bytes:
+            # the planes are views of one buffer laid out like the file's frame: one read for Y, U and V
+            n = os.preadv(self._f.fileno(), [memoryview(flat)], self.frame_offset(i))
+            if n != flat.nbytes:
+                raise EOFError(f"{self.info.path}: short read at frame {i}")
+            return
         self._f.seek(self.frame_offset(i))
         for k, p in enumerate(planes):
             if luma_only and k > 0:

@@ -112,3 +112,39 @@ def test_batch_of_clips_over_two_devices_shares_one_model():
         got = [fr["metrics"]["vmaf"] for fr in batch[k]["frames"]]
         want = [fr["metrics"]["vmaf"] for fr in solo["frames"]]
         assert np.max(np.abs(np.array(got) - np.array(want))) < 1e-9
+
+
+def test_file_ingest_paths_agree(tmp_path):
+    """Raw clip files reach the GPU either through reader threads + a pinned ring (default) or, opt-in, as a CUDA-registered
+    mapping of the page cache (no CPU copy): same frames, same scores, all planes (psnr / ssim stats features on)."""
+    import os
+    import shutil
+    from pqa2_b200 import yuvio
+    w, h, n = 640, 360, 40
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path)
+    d = os.path.join(base, f"b200vmaf_test_{os.getpid()}")
+    os.makedirs(d, exist_ok=True)
+    try:
+        frames = [synth.frame_pair(9, f, w, h, 8) for f in range(n)]
+        rp, dp = os.path.join(d, "r.y4m"), os.path.join(d, "d.y4m")
+        yuvio.write_y4m(rp, (f[0] for f in frames), w, h)
+        yuvio.write_y4m(dp, (f[1] for f in frames), w, h)
+        ri, di = yuvio.probe(rp), yuvio.probe(dp)
+        model = M.resolve_model("vmaf_v0.6.1")
+        opt = engine.EngineOptions(psnr=True, ffmpeg_psnr=True, ffmpeg_ssim=True, batch_frames=8, reader_threads=3,
+                                   devices=(0, 0))
+        ring_src = engine.FileSource(ri, di)
+        assert not ring_src.zero_copy
+        ring = engine.analyze(ring_src, model, opt)
+        direct = engine.analyze(engine.SynthSource(w, h, 8, n, seed=9), model, opt)
+        assert [f["metrics"] for f in ring["frames"]] == [f["metrics"] for f in direct["frames"]]
+        assert np.array_equal(ring["rows"].arr["raw"], direct["rows"].arr["raw"])
+        msrc = engine.FileSource(ri, di, mapped=True)
+        if not msrc.zero_copy:
+            pytest.skip("cudaHostRegister refuses file mappings on this filesystem")
+        mapped = engine.analyze(msrc, model, opt)
+        msrc.release()
+        assert [f["metrics"] for f in mapped["frames"]] == [f["metrics"] for f in ring["frames"]]
+        assert np.array_equal(mapped["rows"].arr["ffssim"], ring["rows"].arr["ffssim"])
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

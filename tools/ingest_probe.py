@@ -20,7 +20,7 @@ for base in ("/dev/shm", "/tmp"):
         ri, di = yuvio.probe(rp), yuvio.probe(dp)
         for all_planes in (False, True):
             opt = engine.EngineOptions(ffmpeg_psnr=all_planes, ffmpeg_ssim=all_planes)
-            for mapped, threads in ((True, 0), (False, 1), (False, 4), (False, 8)):
+            for mapped, threads in ((True, 0), (False, 4), (False, 8), (False, 12), (False, 16)):
                 opt.reader_threads = max(1, threads)
                 src = engine.FileSource(ri, di, mapped=mapped)
                 mode = getattr(src._mapped()[0], "mode", "?") if src.zero_copy else f"ring, {threads} reader threads"

@@ -11,17 +11,22 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORDER = {
-    # the motion blur rides in f_vif_subsample_s1 (fused staging); its SAD follows that kernel
-    "1080p-float": ["psnr_sse_y", "f_vif_stat_s0", "f_vif_subsample_s1", "f_motion_sad", "f_vif_stat_s1",
-                    "f_vif_subsample_s2", "f_vif_stat_s2", "f_vif_subsample_s3", "f_vif_stat_s3", "f_adm_scale0",
+    # psnr=1 reads all three planes; the motion blur rides in f_vif_subsample_s1 (fused staging); its SAD follows that kernel
+    "1080p-float": ["psnr_sse_y", "psnr_sse_u", "psnr_sse_v", "f_vif_stat_s0", "f_vif_subsample_s1", "f_motion_sad",
+                    "f_vif_stat_s1", "f_vif_subsample_s2", "f_vif_stat_s2", "f_vif_subsample_s3", "f_vif_stat_s3", "f_adm_scale0",
                     "f_adm_scale1", "f_adm_scale2", "f_adm_scale3", "ssim_decimate", "ssim_maps", "ms_ssim_maps_s0",
                     "ms_ssim_lpf_s1", "ms_ssim_maps_s1", "ms_ssim_lpf_s2", "ms_ssim_maps_s2", "ms_ssim_lpf_s3",
                     "ms_ssim_maps_s3", "ms_ssim_lpf_s4", "ms_ssim_maps_s4", "f_reduce"],
-    "1080p-int": ["motion_blur", "motion_sad", "vif_stat_s0", "vif_subsample_s1", "vif_stat_s1", "vif_subsample_s2",
-                  "vif_stat_s2", "vif_subsample_s3", "vif_stat_s3", "adm_scale0", "adm_scale1", "adm_scale2", "adm_scale3",
-                  "adm_rows_finish"],
+    # round 2: pyramid level 1 and the motion blur are produced by vif_stat_s0 (fused); the SAD follows the VIF chain
+    "1080p-int": ["vif_stat_s0", "vif_stat_s1", "vif_subsample_s2", "vif_stat_s2", "vif_subsample_s3", "vif_stat_s3",
+                  "motion_sad", "adm_scale0", "adm_scale1", "adm_scale2", "adm_scale3", "adm_rows_finish"],
 }
-ANCHOR = {"1080p-float": "sse_kernel", "1080p-int": "motion_blur_kernel"}
+ORDER["4k-int"] = ORDER["1080p-int"]
+# a kernel that occurs once per frame group, and its name in ORDER
+ANCHOR = {"1080p-float": ("f_motion_sad_kernel", "f_motion_sad"), "1080p-int": ("motion_sad_kernel", "motion_sad"),
+          "4k-int": ("motion_sad_kernel", "motion_sad")}
+FRAMES = {"1080p-float": 32, "1080p-int": 32, "4k-int": 16}
+ROUND = "r02"
 KEYS = [("us", "gpu__time_duration.sum"), ("dram_read_MB", "dram__bytes_read.sum"), ("dram_write_MB", "dram__bytes_write.sum"),
         ("dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
         ("issue_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
@@ -44,11 +49,12 @@ def load(path, wname, frames):
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
     names = [d[ix["Kernel Name"]] for d in data]
-    a = next(i for i, n in enumerate(names) if ANCHOR[wname] in n)
+    anchor, anchor_name = ANCHOR[wname]
+    a = next(i for i, n in enumerate(names) if anchor in n and "f_" + anchor not in n)
     order = ORDER[wname]
     out = {}
     for i, d in enumerate(data):
-        nm = order[(i - a) % len(order)]
+        nm = order[(i - a + order.index(anchor_name)) % len(order)]
         if nm in out:
             continue
         e = {"ncu_kernel": re.sub(r"\(.*", "", names[i]).replace("void <unnamed>::", "").replace("<unnamed>::", ""),
@@ -62,7 +68,7 @@ def load(path, wname, frames):
                 continue
             e[k] = round(v, 3)
         e["bytes"] = int(round((e.get("dram_read_MB", 0) + e.get("dram_write_MB", 0)) * 1e6))
-        e["source"] = f"ncu --set full --clock-control none, {os.path.basename(path)} (profiles/r01_ncu_full_{wname}_{VER}.md)"
+        e["source"] = f"ncu --set full --clock-control none, {os.path.basename(path)} (profiles/{ROUND}_ncu_full_{wname}_{VER}.md)"
         e["pipe_note"] = (f"issue slots {e.get('issue_pct')} % active, FMA pipe {e.get('fma_pipe_pct')} %, ALU pipe "
                           f"{e.get('alu_pipe_pct')} %, FP64 pipe {e.get('fp64_pipe_pct')} %: bound by instruction issue, not by HBM")
         out[nm] = e
@@ -73,23 +79,27 @@ VER = sys.argv[1] if len(sys.argv) > 1 else "v3"
 
 
 def main():
-    frames = 32
     traffic = {}
-    for wname, path in (("1080p-float", f"gpurun_out/raw_float_{VER}.csv"), ("1080p-int", f"gpurun_out/raw_int_{VER}.csv")):
+    old = os.path.join(ROOT, "profiles", f"{ROUND}_traffic.json")
+    if os.path.exists(old):
+        traffic = json.load(open(old))
+    for wname, path in (("1080p-float", f"gpurun_out/raw_float_{VER}.csv"), ("1080p-int", f"gpurun_out/raw_int_{VER}.csv"),
+                        ("4k-int", f"gpurun_out/raw_4k_{VER}.csv")):
         p = os.path.join(ROOT, path)
         if not os.path.exists(p):
             continue
+        frames = FRAMES[wname]
         t = load(p, wname, frames)
         traffic[wname] = t
         cols = ["kernel"] + [k for k, _ in KEYS]
         lines = [f"# ncu --set full --clock-control none, one frame group ({frames} frame pairs per launch) of "
-                 f"`python bench.py --workload {wname} --steps 1 --warmup 3 --no-cpu-baseline --no-e2e`", "",
+                 f"`python bench.py --workload {wname} --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras`", "",
                  " | ".join(cols), " | ".join("---" for _ in cols)]
         for nm in ORDER[wname]:
             if nm in t:
                 lines.append(" | ".join([nm] + [str(t[nm].get(k, "")) for k, _ in KEYS]))
-        open(os.path.join(ROOT, "profiles", f"r01_ncu_full_{wname}_{VER}.md"), "w").write("\n".join(lines) + "\n")
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "r01_traffic.json"), "w"), indent=1)
+        open(os.path.join(ROOT, "profiles", f"{ROUND}_ncu_full_{wname}_{VER}.md"), "w").write("\n".join(lines) + "\n")
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", f"{ROUND}_traffic.json"), "w"), indent=1)
     print({w: len(t) for w, t in traffic.items()})
 
 

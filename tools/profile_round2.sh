@@ -1,0 +1,19 @@
+#!/bin/bash
+# Round-2 evidence run on the GPU box: the plain bench line first, then -- only after it exited -- the ncu launch list of
+# the same command and one `--set full` capture of a whole frame group per workload.  Usage: tools/profile_round2.sh <tag>
+TAG=${1:-v1}
+O=gpurun_out
+python bench.py --steps 20 --warmup 3 > $O/r02_bench_$TAG.json 2> $O/r02_bench_$TAG.err || exit 1
+python bench.py --impl reference --steps 2 --warmup 1 > $O/r02_bench_reference_$TAG.json 2>> $O/r02_bench_$TAG.err
+X="--steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras"
+# numbers printed under ncu are never bench values
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/r02_launches_$TAG.csv \
+    python bench.py $X > $O/ncu_launches_$TAG.log 2>&1
+ncu --set full --clock-control none --launch-skip 1330 -c 29 -f -o $O/full_float_$TAG python bench.py $X > $O/ncu_full_float_$TAG.log 2>&1
+ncu -i $O/full_float_$TAG.ncu-rep --page raw --csv > $O/raw_float_$TAG.csv
+ncu --set full --clock-control none --launch-skip 590 -c 14 -f -o $O/full_int_$TAG python bench.py --workload 1080p-int $X > $O/ncu_full_int_$TAG.log 2>&1
+ncu -i $O/full_int_$TAG.ncu-rep --page raw --csv > $O/raw_int_$TAG.csv
+ncu --set full --clock-control none --launch-skip 590 -c 14 -f -o $O/full_4k_$TAG python bench.py --workload 4k-int $X > $O/ncu_full_4k_$TAG.log 2>&1
+ncu -i $O/full_4k_$TAG.ncu-rep --page raw --csv > $O/raw_4k_$TAG.csv
+rm -f $O/full_float_$TAG.ncu-rep $O/full_int_$TAG.ncu-rep $O/full_4k_$TAG.ncu-rep
+ls -la $O | tail -12
