@@ -563,20 +563,44 @@ def measure_sharded_4k(cx: Ctx, pool: Pool) -> dict:
             return out
 
         D.analyze_distributed(pool.clip(min(n, 64 * cx.world)), model, opt, device=cx.local, session=sess,
-                              svr_device=cx.local)                 # warm-up: contexts, first launches
-        for _ in range(3):
-            cx.barrier()
-            t0 = time.perf_counter()
-            r = D.analyze_distributed(clip, model, opt, device=cx.local, shard_fn=timed_shard, svr_device=cx.local)
-            dt = time.perf_counter() - t0            # rank 0 returns after the gather, the SVR and the pooling
-            times.append(cx.max_over_ranks(dt))
-            res = r if r is not None else res
+                              svr_device=cx.local)                 # warm-up: contexts, first launches, first gather
+        # chunk lengths proportional to what each rank sustains while all ranks upload at once (dist.calibrate): the
+        # box's GPUs do not see the same host-to-device bandwidth under load (tools/h2d_concurrent.py)
+        weights = D.calibrate(clip, model, opt, device=cx.local, session=sess) if cx.world > 1 else None
+        equal_times = []
+        for policy in (("equal", None), ("weighted", weights)) if cx.world > 1 else (("equal", None),):
+            for _ in range(3 if policy[0] == "weighted" or cx.world == 1 else 2):
+                cx.barrier()
+                t0 = time.perf_counter()
+                r = D.analyze_distributed(clip, model, opt, device=cx.local, shard_fn=timed_shard, svr_device=cx.local,
+                                          weights=policy[1])
+                dt = time.perf_counter() - t0        # rank 0 returns after the gather, the SVR and the pooling
+                (equal_times if policy[0] == "equal" and cx.world > 1 else times).append(cx.max_over_ranks(dt))
+                res = r if r is not None else res
+        # the same chunks with the frames already resident in HBM (device-timed, max over ranks): the compute path alone
+        from pqa2_b200 import _lib as L
+        from pqa2_b200.extractor import FeatureExtractor
+        a, b = D.rank_range(n, cx.rank, cx.world)
+        with FeatureExtractor(pool.w, pool.h, pool.bpc, 0, engine.feature_mask(model, opt), cx.local) as fx:
+            for rep in range(2):
+                fx.reset()
+                cx.barrier()
+                fx.timer_mark(0)
+                for i in range(max(a - 1, 0), b):
+                    fx.submit_device(i, pool.dev_planes(i, 0), pool.dev_planes(i, 1),
+                                     (L.FRAME_FIRST if i == max(a - 1, 0) else 0) | (L.FRAME_LEAD_IN if i < a else 0))
+                fx.timer_mark(1)
+                fx.flush()
+                resident_s = cx.max_over_ranks(fx.timer_elapsed_ms() / 1000.0)
         rec = None
         if cx.rank == 0:
             dt = min(times)
             per_frame = 2 * pool.frame_bytes
             rec = {"value": n / dt, "unit": "frames/s", "frames": n, "n_gpus": cx.world, "scaling": "strong",
                    "seconds": dt, "runs": [round(t, 4) for t in times], "rank0_shard_seconds": [round(t, 4) for t in shard_s],
+                   "resident_value": n / resident_s,
+                   "resident_note": "the same contiguous chunks + lead-in frames with the clip already in HBM, device-timed, "
+                                    "max over ranks: the compute path without the host-to-device ingest",
                    "workload": f"configs[2]: ONE 3840x2160 yuv420p10le clip of {n} frames (a pinned pool of {pool.P} distinct "
                                f"frame pairs, cycled), {wl['model']}, contiguous frame chunks + one-frame lead-in per rank, "
                                "rows gathered on rank 0",
@@ -585,6 +609,10 @@ def measure_sharded_4k(cx: Ctx, pool: Pool) -> dict:
                    "timer": "host wall clock around dist.analyze_distributed (H2D of every frame, kernels, row gather, "
                             "motion2 / SVR / pooling on rank 0); max over ranks, best of 2"}
             if cx.world > 1:
+                rec["split"] = "chunk lengths proportional to each rank's calibrated rate (dist.calibrate)"
+                rec["calibrated_fps_per_rank"] = [round(x, 1) for x in weights]
+                rec["equal_split_value"] = n / min(equal_times)
+                rec["equal_split_runs"] = [round(t, 4) for t in equal_times]
                 # the same clip on rank 0's GPU alone: every per-frame value must be bit-identical (integer accumulators)
                 t0 = time.perf_counter()
                 one = sess.analyze(clip, model, opt)
@@ -614,7 +642,9 @@ def measure_batch(cx: Ctx, pool: Pool) -> dict:
     nclips, nfr = cx.args.batch_clips, BATCH_FRAMES
     clips = [pool.clip(nfr, offset=5 * k, stride=1 + k % 3) for k in range(nclips)]
     with engine.Engine() as sess:
-        sess.analyze(pool.clip(64), model, opt)                               # warm-up
+        # warm-up: the contexts and first launches, and the process group's first object gather (a fresh NCCL communicator
+        # sets up its channels lazily -- about a second at 8 ranks -- which is not the sweep's cost)
+        D.analyze_batch_distributed([pool.clip(64) for _ in range(cx.world)], model, opt, device=cx.local, session=sess)
         cx.barrier()
         t0 = time.perf_counter()
         out = D.analyze_batch_distributed(clips, model, opt, device=cx.local, session=sess)

@@ -12,9 +12,9 @@ import threading
 from . import engine, report
 
 
-def rank_range(n_frames: int, rank: int, world: int, first: int = 0):
+def rank_range(n_frames: int, rank: int, world: int, first: int = 0, weights=None):
     """[start, end) of this rank's chunk (may be empty when world > n_frames)."""
-    r = engine.shard_ranges(n_frames, world)
+    r = engine.shard_ranges(n_frames, world, weights)
     if rank >= len(r):
         return (first + n_frames, first + n_frames)
     return (first + r[rank][0], first + r[rank][1])
@@ -49,17 +49,47 @@ def max_over_ranks(value: float, group=None, device=None) -> float:
     return float(t.item())
 
 
+def calibrate(src, model, opt: engine.EngineOptions | None = None, device: int = 0, group=None, frames: int = 0,
+              session: "engine.Engine | None" = None) -> list:
+    """Per-rank frames/s of a short trial, all ranks at once: the weights for ``analyze_distributed(weights=...)``.
+
+    Every rank scores the same first ``frames`` frames of ``src`` (default: four launch groups) on its own GPU while all
+    the others do the same, so the number reflects what the rank gets when the host's PCIe links are shared -- on the
+    8 x B200 box four GPUs hang off one host bridge and see ~30 GB/s each under load, against 50 GB/s alone
+    (tools/h2d_concurrent.py).  Call on every rank; returns the same list everywhere."""
+    import time
+    opt = opt or engine.EngineOptions()
+    rank, world = _world(group)
+    if world == 1:
+        return [1.0]
+    import torch
+    import torch.distributed as dist
+    n = min(src.nb_frames, frames or 64)
+    mask = engine.feature_mask(model, opt)
+    _default_shard_fn(src, model, opt, device, 0, min(n, 8), mask, session)          # contexts, first launches
+    dist.barrier(group)
+    t0 = time.perf_counter()
+    _default_shard_fn(src, model, opt, device, 0, n, mask, session)
+    fps = n / (time.perf_counter() - t0)
+    nccl = dist.get_backend(group) == "nccl"
+    t = torch.tensor([fps], dtype=torch.float64, device=f"cuda:{device}" if nccl else "cpu")
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return [float(x.item()) for x in out]
+
+
 def analyze_distributed(src, model, opt: engine.EngineOptions | None = None, device: int = 0, group=None,
-                        shard_fn=None, svr_device=None, session: "engine.Engine | None" = None):
+                        shard_fn=None, svr_device=None, session: "engine.Engine | None" = None, weights=None):
     """Call on every rank.  Returns the libvmaf log dict on rank 0 and None elsewhere.
 
     ``shard_fn(src, model, opt, device, start, end, mask) -> {frame_index: row}`` computes one shard
     (default: the CUDA extractors on ``device``); the CPU tests inject a stub.  ``session`` keeps this rank's
-    CUDA context alive between clips.  Without an initialised process group the call is the world-size-1 case."""
+    CUDA context alive between clips.  ``weights`` (from ``calibrate``; identical on every rank) sizes the chunks by each
+    rank's sustained rate.  Without an initialised process group the call is the world-size-1 case."""
     opt = opt or engine.EngineOptions()
     rank, world = _world(group)
     n = src.nb_frames
-    start, end = rank_range(n, rank, world)
+    start, end = rank_range(n, rank, world, weights=weights)
     mask = engine.feature_mask(model, opt)
     if end <= start:
         mine = {}

@@ -265,10 +265,20 @@ def feature_mask(model: VmafModel, opt: EngineOptions) -> int:
     return m | opt.extra_features
 
 
-def shard_ranges(n_frames: int, n_shards: int):
-    """Contiguous chunks [start, end) per shard."""
+def shard_ranges(n_frames: int, n_shards: int, weights=None):
+    """Contiguous chunks [start, end) per shard.  ``weights`` (one positive number per shard, e.g. the
+    frames/s each GPU sustained in a calibration pass) makes the chunk lengths proportional to them: on a box whose GPUs
+    do not see the same host-to-device bandwidth, equal chunks leave the fast ones idle while the slow ones finish."""
     n_shards = max(1, min(n_shards, max(n_frames, 1)))
-    return [(g * n_frames // n_shards, (g + 1) * n_frames // n_shards) for g in range(n_shards)]
+    if weights is None or len(weights) != n_shards or not all(w > 0 for w in weights):
+        return [(g * n_frames // n_shards, (g + 1) * n_frames // n_shards) for g in range(n_shards)]
+    total = float(sum(weights))
+    cuts, acc = [0], 0.0
+    for w in weights[:-1]:
+        acc += w
+        cuts.append(min(n_frames, max(cuts[-1], int(round(n_frames * acc / total)))))
+    cuts.append(n_frames)
+    return [(cuts[g], cuts[g + 1]) for g in range(n_shards)]
 
 
 _FIRST_KICK = 8

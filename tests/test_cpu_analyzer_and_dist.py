@@ -239,3 +239,14 @@ def test_column_pooling_equals_the_per_frame_walk():
         col = rng.uniform(0.0, 100.0, n)
         assert engine._pool_column(col) == report.pool(col.tolist())
     assert engine._pool_column(np.zeros(0)) == report.pool([])
+
+
+def test_weighted_shard_ranges():
+    """engine.shard_ranges with per-shard rates: contiguous, complete, proportional; degenerate weights fall back to equal."""
+    r = engine.shard_ranges(3600, 8, [24, 24, 24, 24, 36, 36, 36, 36])
+    assert r[0][0] == 0 and r[-1][1] == 3600 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+    lens = [b - a for a, b in r]
+    assert lens[:4] == [360] * 4 and lens[4:] == [540] * 4
+    assert engine.shard_ranges(10, 3, [1, 0, 1]) == engine.shard_ranges(10, 3)
+    assert engine.shard_ranges(5, 2, [1.0, 1.0]) == [(0, 2), (2, 5)] or engine.shard_ranges(5, 2, [1.0, 1.0]) == [(0, 3), (3, 5)]
+    assert D.rank_range(3600, 5, 8, weights=[24, 24, 24, 24, 36, 36, 36, 36]) == (1980, 2520)
