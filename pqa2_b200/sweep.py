@@ -58,62 +58,3 @@ def run_sweep(clips: list, model: VmafModel, out_dir: str, names: list | None = 
         results.append(summary)
     combined = report.write_combined_csv(os.path.join(out_dir, f"combined_results_{stamp}.csv"), rows)
     return {"results": results, "combined_csv": combined}
-
-
-def read_pairs(path: str) -> list:
-    """Pairs file: CSV rows ``name,reference,distorted`` (a header row with those words is skipped); relative paths are
-    resolved against the file's directory."""
-    import csv
-    base = os.path.dirname(os.path.abspath(path))
-    out = []
-    with open(path, newline="") as f:
-        for row in csv.reader(f):
-            row = [c.strip() for c in row]
-            if len(row) < 3 or not row[0] or row[0].startswith("#") or row[1].lower() in ("reference", "ref"):
-                continue
-            out.append((row[0], os.path.join(base, row[1]), os.path.join(base, row[2])))
-    return out
-
-
-def main(argv=None) -> int:
-    """python -m pqa2_b200.sweep PAIRS.csv [--out DIR] [--model vmaf_v0.6.1] [--gpus 0,1,...] [--align-bookends]"""
-    import argparse
-    import sys
-    from . import _lib as L
-    from . import model as M
-    from . import yuvio
-    ap = argparse.ArgumentParser(prog="python -m pqa2_b200.sweep", description=main.__doc__)
-    ap.add_argument("pairs")
-    ap.add_argument("--out", default="sweep_results")
-    ap.add_argument("--model", default="vmaf_v0.6.1")
-    ap.add_argument("--gpus", default=None)
-    ap.add_argument("--align-bookends", action="store_true", help="every distorted clip is a capture with white bookends")
-    a = ap.parse_args(argv)
-    pairs = read_pairs(a.pairs)
-    if not pairs:
-        print("error: no pairs in", a.pairs, file=sys.stderr)
-        return 1
-    n = L.load().bv_device_count()
-    if n < 1:
-        print("error: no CUDA device (the B200 VMAF engine has no CPU fallback)", file=sys.stderr)
-        return 1
-    devices = [int(x) for x in a.gpus.split(",")] if a.gpus else list(range(n))
-    clips, names = [], []
-    for name, ref, dis in pairs:
-        if a.align_bookends:
-            from . import alignment
-            res = alignment.align_by_bookends(ref, dis, device=devices[0])
-            clips.append(res["source"])
-        else:
-            clips.append(engine.FileSource(yuvio.probe(ref), yuvio.probe(dis)))
-        names.append(name)
-    out = run_sweep(clips, M.resolve_model(a.model), a.out, names, devices=devices)
-    for r in out["results"]:
-        print(r["test_name"], "error: " + r["error"] if "error" in r else "%.6f" % r["vmaf_score"])
-    print("combined:", out["combined_csv"])
-    return 0 if all("error" not in r for r in out["results"]) else 2
-
-
-if __name__ == "__main__":
-    import sys
-    sys.exit(main())

@@ -175,11 +175,3 @@ def test_sweep_writes_the_artifacts_the_history_tab_indexes(tmp_path):
     rows = list(csv.reader(open(out["combined_csv"])))
     assert len(rows) == 4 and [x[0] for x in rows[1:]] == ["a", "b", "c"]
     assert float(rows[1][2]) == pytest.approx(out["results"][0]["vmaf_score"], abs=5e-5)
-
-
-def test_sweep_pairs_file(tmp_path):
-    from pqa2_b200 import sweep
-    p = tmp_path / "pairs.csv"
-    p.write_text("name,reference,distorted\n# comment\nclipA, a/ref.y4m, a/dis.y4m\nclipB,/abs/ref.y4m,/abs/dis.y4m\n\n")
-    got = sweep.read_pairs(str(p))
-    assert got == [("clipA", str(tmp_path / "a/ref.y4m"), str(tmp_path / "a/dis.y4m")), ("clipB", "/abs/ref.y4m", "/abs/dis.y4m")]
