@@ -11,7 +11,9 @@ from __future__ import annotations
 import csv
 import math
 
-VERSION = "b200vmaf-0.1 (libvmaf 3.0.0 semantics)"
+# What the log's "version" field says (libvmaf writes its own version there; the reference shows it as the model /
+# engine string, app/vmaf_analyzer.py:834-838).  It names this engine and states what its numbers were checked against.
+VERSION = "b200vmaf-0.2 (restates libvmaf 3.0.0; parity checked against the in-repo CPU oracle only)"
 
 
 def pool(values) -> dict:
