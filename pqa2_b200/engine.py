@@ -420,6 +420,14 @@ class Engine:
     def analyze(self, src, model, opt=None, progress_cb=None, cancel=None, frame_range=None):
         return analyze(src, model, opt, progress_cb, cancel, frame_range, session=self)
 
+    def retain(self, width: int, height: int, bpc: int):
+        """Free every context and ring that was built for another picture geometry (call between analyses, never
+        during one): a long-lived session that sees many resolutions would otherwise keep 1-7 GB per GPU for each."""
+        with self._lock:
+            for key in [k for k in self._fx if k[2:5] != (width, height, bpc)]:
+                self._fx.pop(key).close()
+                self._rings.pop(key, None)
+
     def close(self):
         with self._lock:
             for fx in self._fx.values():

@@ -225,7 +225,7 @@ class VMAFAnalyzer(QObject):
                                    float_motion=bool(self.enable_motion_score or self.enable_temporal_features))
         if ref_info.decoder == "cv2" or dis_info.decoder == "cv2":
             # container decode is sequential (seeking is not frame-exact): one shard, one decoder per file
-            opt.devices = devices[:1]
+            devices = tuple(devices)[:1]
         src = engine.FileSource(ref_info, dis_info)
         last = [-1]
 
@@ -235,6 +235,10 @@ class VMAFAnalyzer(QObject):
                 last[0] = pct
                 self.analysis_progress.emit(pct)
 
+        self._engine.retain(ref_info.width, ref_info.height, ref_info.bpc)
+        # a GPU pays for its context and pipeline fill only with a few launch groups of its own: at least 128 frames each
+        devices = tuple(devices)[:max(1, min(len(devices), src.nb_frames // 128))]
+        opt.devices = devices
         self.status_update.emit(f"Scoring {src.nb_frames} frames on {len(devices)} GPU(s)")
         try:
             self.last_ingest = "mapped" if src.zero_copy else "ring"
