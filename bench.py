@@ -720,12 +720,20 @@ def two_gpus_in_one_process_check(cx: Ctx, pool: Pool) -> dict:
     skipped there; with N >= 2 GPUs visible rank 0 runs the same check here: one process, one thread + context per GPU."""
     from pqa2_b200 import engine, model as M
     model = M.resolve_model("vmaf_v0.6.1")
-    clip = pool.clip(96)
-    one = engine.analyze(clip, model, engine.EngineOptions(devices=(0,)))
-    two = engine.analyze(clip, model, engine.EngineOptions(devices=(0, 1)))
-    same = [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in two["frames"]] and \
-        np.array_equal(one["rows"].arr["raw"], two["rows"].arr["raw"])
-    return {"frames": 96, "devices": [0, 1], "identical": bool(same)}
+    out = {"devices": [0, 1]}
+    # 96 frames: two fixed shares; 4096 frames: chunks of 512 pulled from a shared counter (engine.analyze dynamic_chunk)
+    for n in (96, 4096):
+        clip = pool.clip(n)
+        one = engine.analyze(clip, model, engine.EngineOptions(devices=(0,)))
+        t0 = time.perf_counter()
+        two = engine.analyze(clip, model, engine.EngineOptions(devices=(0, 1)))
+        dt = time.perf_counter() - t0
+        same = [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in two["frames"]] and \
+            np.array_equal(one["rows"].arr["raw"], two["rows"].arr["raw"])
+        out[f"identical_{n}_frames"] = bool(same)
+        out[f"fps_{n}_frames_cold"] = n / dt          # includes creating both contexts: no session here
+    out["identical"] = all(v for k, v in out.items() if k.startswith("identical_"))
+    return out
 
 
 # --------------------------------------------------------------------------------------------

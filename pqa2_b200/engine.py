@@ -40,6 +40,7 @@ class EngineOptions:
     svr_on_device: bool = True
     extra_features: int = 0          # extra _lib.FEAT_* bits
     fast_float: bool = False         # float models only, opt-in: contracted / folded-tap stencils (bv_opts.fast_float)
+    dynamic_chunk: int = 512         # frames per chunk when several GPUs share a long clip (>= 4 chunks per GPU); 0 = fixed shares
     reader_threads: int = 0          # file readers per shard (pinned-ring path); 0 = auto (cores / shards, 2 .. 16)
     float_motion: bool = False       # `feature=name=motion` (app/vmaf_analyzer.py:388-402): libvmaf's float motion
                                      # extractor next to the model's own features -> `motion`, `motion2` in the log
@@ -737,17 +738,45 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
     holders: list = []
     t0 = time.perf_counter()
     threads = []
-    for k, (dev, (a, b)) in enumerate(zip(devices, ranges)):
-        if b <= a:
-            continue
-        # a frame_range is scored as libvmaf would score the trimmed clip: its first frame has no predecessor
-        # (motion = 0), so only the shards after the first one get a lead-in frame
-        th = threading.Thread(target=_run_shard, args=(src, model, opt, dev, a, b, mask, rows, progress, cancel,
-                                                       errors, holders, session, k, a > first), daemon=True)
-        th.start()
-        threads.append(th)
+    # Long clips on several GPUs: the devices pull chunks of `dynamic_chunk` frames from a shared counter instead of
+    # each getting one fixed share.  The GPUs of one box do not see the same host-to-device bandwidth under load (four
+    # of the eight B200s share a host bridge: ~24 vs ~36 GB/s each, tools/h2d_concurrent.py), and with equal shares the
+    # fast ones idle while the slow ones finish.  Every chunk after the first carries its own lead-in frame, so the
+    # results are the same bits; sequential sources (container decode) keep their single shard.
+    chunk = opt.dynamic_chunk
+    own_session = None
+    if (len(devices) > 1 and chunk > 0 and n >= 4 * len(devices) * chunk and not getattr(src, "sequential", False)):
+        if session is None:
+            session = own_session = Engine()            # contexts must survive from chunk to chunk
+        nxt = [first]
+
+        def worker(k, dev):
+            while not cancel.is_set():
+                with lock:
+                    a = nxt[0]
+                    nxt[0] = b = min(last, a + chunk)
+                if a >= last:
+                    return
+                _run_shard(src, model, opt, dev, a, b, mask, rows, progress, cancel, errors, holders, session, k, a > first)
+
+        for k, dev in enumerate(devices):
+            th = threading.Thread(target=worker, args=(k, dev), daemon=True)
+            th.start()
+            threads.append(th)
+    else:
+        for k, (dev, (a, b)) in enumerate(zip(devices, ranges)):
+            if b <= a:
+                continue
+            # a frame_range is scored as libvmaf would score the trimmed clip: its first frame has no predecessor
+            # (motion = 0), so only the shards after the first one get a lead-in frame
+            th = threading.Thread(target=_run_shard, args=(src, model, opt, dev, a, b, mask, rows, progress, cancel,
+                                                           errors, holders, session, k, a > first), daemon=True)
+            th.start()
+            threads.append(th)
     for th in threads:
         th.join()
+    if own_session is not None:
+        own_session.close()
     for k, e in errors:               # an engine error wins over the cancellation it triggered in the sibling shards
         if k == "error":
             raise e

@@ -222,3 +222,34 @@ def test_file_source_reader_threads_fill_the_ring_in_order(fake, tmp_path):
     got = sorted((idx, content) for fx in fake.instances for idx, content, fl in fx.frames if not fl & L.FRAME_LEAD_IN)
     assert got == [(i, i % 251) for i in range(n)]
     assert [fr["frameNum"] for fr in res["frames"]] == list(range(n))
+
+
+def test_session_keeps_contexts_per_geometry_and_retain_drops_the_others(fake):
+    model = M.resolve_model("vmaf_v0.6.1")
+    closed = []
+    fake.close = lambda self: closed.append(self)
+    with engine.Engine() as sess:
+        sess.analyze(Clip(10), model, _opt())
+        sess.analyze(Clip(12), model, _opt())                    # same geometry: the context is reused, not rebuilt
+        assert len(fake.instances) == 1
+
+        class Small(Clip):
+            width, height = 48, 32
+        sess.analyze(Small(6), model, _opt())
+        assert len(fake.instances) == 2 and not closed
+        sess.retain(48, 32, 8)                                   # what VMAFAnalyzer does before the next analysis
+        assert closed == [fake.instances[0]] and list(k[2:5] for k in sess._fx) == [(48, 32, 8)]
+
+
+def test_long_clip_on_several_devices_is_dealt_in_chunks(fake):
+    """>= 4 chunks per device: the devices pull chunks from a shared counter; every chunk after the first starts with its
+    lead-in frame; the log is identical to the single-device one (motion2 across every chunk border)."""
+    model = M.resolve_model("vmaf_v0.6.1")
+    n = 400
+    one = engine.analyze(Clip(n), model, _opt(devices=(0,)))
+    fake.instances.clear()
+    dyn = engine.analyze(Clip(n), model, _opt(devices=(0, 0), dynamic_chunk=40))
+    assert [fr["metrics"] for fr in dyn["frames"]] == [fr["metrics"] for fr in one["frames"]]
+    assert len(fake.instances) == 2                                  # one context per device, reused from chunk to chunk
+    fixed = engine.analyze(Clip(n), model, _opt(devices=(0, 0), dynamic_chunk=0))
+    assert [fr["metrics"] for fr in fixed["frames"]] == [fr["metrics"] for fr in one["frames"]]
