@@ -148,3 +148,16 @@ def test_file_ingest_paths_agree(tmp_path):
         assert np.array_equal(mapped["rows"].arr["ffssim"], ring["rows"].arr["ffssim"])
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_dynamic_chunks_match_one_shard():
+    """engine.analyze deals a long clip to its devices in chunks (here two contexts on one GPU, chunks of 24 frames so that
+    chunk borders fall inside launch groups): same bits as one shard, integer and float model."""
+    w, h, n = 320, 180, 200
+    src = engine.SynthSource(w, h, 8, n, seed=23, chroma=0)
+    for name in ("vmaf_v0.6.1", "vmaf_float_v0.6.1"):
+        model = M.resolve_model(name)
+        one = engine.analyze(src, model, engine.EngineOptions(devices=(0,)))
+        dyn = engine.analyze(src, model, engine.EngineOptions(devices=(0, 0), dynamic_chunk=24))
+        assert [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in dyn["frames"]]
+        assert np.array_equal(one["rows"].arr["raw"], dyn["rows"].arr["raw"])
