@@ -267,3 +267,39 @@ def vif_float(ref_f: np.ndarray, dis_f: np.ndarray, egl: float = 100.0, row_acc=
             num[scale] = float(nv.astype(np.float64).sum())
             den[scale] = float(dv.astype(np.float64).sum())
     return num, den
+
+
+# ---------------------------------------------------------------------------------------------
+# integer ADM, scale 0: the db2 wavelet decomposition (integer_adm.c adm_dwt2_8 / adm_dwt2_16)
+# ---------------------------------------------------------------------------------------------
+DWT_LO = [15826, 27411, 7345, -4240]
+DWT_HI = [-4240, -7345, 27411, -15826]
+
+
+def _dwt_index(n_out: int, n: int) -> np.ndarray:
+    """input indices 2i-1, 2i, 2i+1, 2i+2 of output i, folded back at both ends: -1 -> 1; n + k -> n - 1 - k"""
+    idx = 2 * np.arange(n_out)[:, None] + np.arange(-1, 3)[None, :]
+    idx = np.abs(idx)
+    return np.where(idx >= n, 2 * n - idx - 1, idx)
+
+
+def adm_dwt_scale0(luma: np.ndarray, bpc: int = 8) -> np.ndarray:
+    """-> int64 [4, (h+1)//2, (w+1)//2]: bands a, v, h, d of the picture as int16 values.  Vertical pass: the low band is
+    re-centred by subtracting sum(lo) * 2^(bpc-1) (pixels are unsigned), both bands rounded with 2^(bpc-1) and shifted
+    by bpc; horizontal pass: (acc + 32768) >> 16.  a = lo.lo, v = hi along x of the vertical low band, h = lo along x
+    of the vertical high band, d = hi.hi."""
+    p = luma.astype(np.int64)
+    h, w = p.shape
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    iy, jx = _dwt_index(oh, h), _dwt_index(ow, w)
+    half = 1 << (bpc - 1)
+    rows = p[iy]                                          # [oh, 4, w]
+    lo = (np.tensordot(rows, np.array(DWT_LO), axes=([1], [0])) - sum(DWT_LO) * half + half) >> bpc
+    hi = (np.tensordot(rows, np.array(DWT_HI), axes=([1], [0])) + half) >> bpc
+    to16 = lambda a: ((a + 32768) % 65536) - 32768        # the C code stores these in int16_t
+    lo, hi = to16(lo), to16(hi)
+    out = []
+    for src, taps in ((lo, DWT_LO), (lo, DWT_HI), (hi, DWT_LO), (hi, DWT_HI)):
+        cols = src[:, jx]                                 # [oh, ow, 4]
+        out.append(to16((cols @ np.array(taps) + 32768) >> 16))
+    return np.stack(out)

@@ -82,3 +82,14 @@ def test_float_vif_kernel_tables_are_the_normalised_gaussians():
         want = np.ctypeslib.as_array(oracle._flib().orc_f_vif_filter(s), (n,))
         np.testing.assert_allclose(MN._gauss(n), want, rtol=0, atol=1e-7)
         assert abs(float(want.astype(np.float64).sum()) - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("seed,w,h,bpc", [(3, 176, 144, 8), (5, 161, 97, 8), (8, 208, 120, 10), (9, 242, 137, 12)])
+def test_integer_adm_scale0_wavelet_bands_agree(seed, w, h, bpc):
+    """The db2 decomposition every later ADM stage builds on: a, v, h, d of the reference picture, value for value."""
+    rp, dp = synth.frame_pair(seed, 0, w, h, bpc, chroma=False)
+    got = oracle.adm(rp[0], dp[0], bpc, want_bands=True)["ref_bands_s0"]
+    want = MN.adm_dwt_scale0(rp[0], bpc)
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+    assert np.abs(want[1:]).max() > 0                     # the detail bands are not trivially zero
