@@ -18,8 +18,8 @@ ncu -i $O/full_4k_$TAG.ncu-rep --page raw --csv > $O/raw_4k_$TAG.csv
 rm -f $O/full_float_$TAG.ncu-rep $O/full_int_$TAG.ncu-rep $O/full_4k_$TAG.ncu-rep
 ls -la $O | tail -12
 # source-level capture of the two dominant kernels (dynamic SASS opcode histogram, per-line counters)
-tools/prof_src.sh 1080p-int "vif_stat_kernel<unsigned char" 1 r02_int_vif0 || true
-tools/prof_src.sh 1080p-float "f_vif_stat_kernel<unsigned char" 1 r02_f_vif0 || true
+tools/prof_src.sh 1080p-int "^vif_stat_kernel" 1 r02_int_vif0 || true
+tools/prof_src.sh 1080p-float "^f_vif_stat_kernel" 1 r02_f_vif0 || true
 python tools/sass_hist.py $O/src_r02_int_vif0.csv 66355200 > $O/r02_sass_dyn_vif_stat_s0.txt 2>&1 || true
 python tools/sass_hist.py $O/src_r02_f_vif0.csv 66355200 > $O/r02_sass_dyn_f_vif_stat_s0.txt 2>&1 || true
 rm -f $O/src_r02_int_vif0.csv $O/src_r02_f_vif0.csv
