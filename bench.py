@@ -20,7 +20,7 @@ Headline workload (identical at every N): configs[1].  Next to it, in the same J
   file_e2e       (N = 1)  the drop-in call itself: VMAFAnalyzer.analyze_videos() on a 300-frame 1080p .y4m pair
 
 Workloads (BASELINE.json `configs`):
-  1080p-float  configs[1]: 1080p yuv420p 8-bit, vmaf_float_v0.6.1 + psnr (y, cb, cr) + float_ssim + float_ms_ssim
+  1080p-float  configs[1]: 1080p yuv420p 8-bit, vmaf_float_v0.6.1 + psnr + float_ssim + float_ms_ssim
   1080p-int    configs[0] shape: 1080p 8-bit, vmaf_v0.6.1 (integer extractors)
   4k-int       configs[2]: 2160p yuv420p10le, vmaf_4k_v0.6.1
 """
@@ -291,11 +291,11 @@ def wl_dtype(wl) -> str:
 
 
 def bench_config(wl, wname, fps, n_gpus) -> dict:
-    chroma = wl["psnr"]
+    chroma = False          # libvmaf psnr=1 is psnr_y (enable_chroma=false through FFmpeg): every enabled feature reads luma
     bps = 1 if wl["bpc"] == 8 else 2
     mb = wl["pool"] * 2 * wl["w"] * wl["h"] * bps * (1.5 if chroma else 1.0) / 1e6
     return {"workload": f"{wname}: {wl['cfg']} -- {wl['w']}x{wl['h']} yuv420p {wl['bpc']}-bit, model {wl['model']}"
-                        + (" + psnr (y, cb, cr)" if wl["psnr"] else "") + (" + float_ssim" if wl["ssim"] else "")
+                        + (" + psnr" if wl["psnr"] else "") + (" + float_ssim" if wl["ssim"] else "")
                         + (" + float_ms_ssim" if wl["ms_ssim"] else ""),
             "frames_per_step_per_gpu": fps, "pool_frames_per_gpu": wl["pool"],
             "planes": "Y, Cb, Cr (psnr=1 reads all three)" if chroma else "Y (every enabled feature reads luma only)",
@@ -783,7 +783,9 @@ def main() -> int:
 
     # ---- headline workload
     t0 = time.perf_counter()
-    pool = Pool(wl["w"], wl["h"], wl["bpc"], wl["pool"], 100, wl["psnr"], local)      # the same clip on every rank
+    # the same clip on every rank; at N = 1 with chroma planes, which only the file_e2e record (FFmpeg psnr / ssim stats
+    # files over Y, Cb, Cr) reads -- libvmaf's psnr=1 is psnr_y, so the headline uploads luma only
+    pool = Pool(wl["w"], wl["h"], wl["bpc"], wl["pool"], 100, world == 1 and args.workload == "auto" and not args.no_extras, local)
     if rank == 0:
         log(f"[bench] synthesised {wl['pool']} frame pairs {wl['w']}x{wl['h']} {wl['bpc']}-bit in {time.perf_counter() - t0:.1f}s")
     head = measure_workload(cx, wname, wl, pool, args.steps, args.warmup, True, not args.no_e2e)

@@ -27,7 +27,9 @@ from .yuvio import EndOfClip
 @dataclass
 class EngineOptions:
     n_subsample: int = 1
-    psnr: bool = False               # libvmaf `psnr=1`   -> psnr_y
+    psnr: bool = False               # libvmaf `psnr=1`   -> psnr_y (FFmpeg's libvmaf filter maps the option to the `psnr`
+                                     # extractor with enable_chroma=false: SURVEY.md Appendix A.8)
+    psnr_chroma: bool = False        # `feature=name=psnr` without that flag -> psnr_y, psnr_cb, psnr_cr
     ssim: bool = False               # libvmaf `ssim=1`   -> float_ssim
     ms_ssim: bool = False            # libvmaf `ms_ssim=1`-> float_ms_ssim
     ffmpeg_psnr: bool = False        # FFmpeg `psnr` filter stats (all planes)
@@ -251,8 +253,10 @@ def _plane_shapes(src: FrameSource):
 
 def feature_mask(model: VmafModel, opt: EngineOptions) -> int:
     m = L.FEAT_VMAF_FLOAT if model.is_float else L.FEAT_VMAF_INT
-    if opt.psnr:
-        m |= L.FEAT_PSNR_Y | L.FEAT_PSNR_UV      # psnr_y, psnr_cb, psnr_cr (chroma bits are inert for luma-only sources)
+    if opt.psnr or opt.psnr_chroma:
+        m |= L.FEAT_PSNR_Y
+    if opt.psnr_chroma:
+        m |= L.FEAT_PSNR_UV                      # inert for luma-only sources
     if opt.ssim:
         m |= L.FEAT_FLOAT_SSIM
     if opt.ms_ssim:
@@ -564,9 +568,11 @@ def _build_frames_block(rows: Rows, model: VmafModel, opt: EngineOptions, device
         cols.append((f"{pre}motion", motion))
     cols += [(f"{pre}vif_scale{k}{vs}", vif[:, k]) for k in range(4)]
     opt_cols = []
-    if opt.psnr or opt.ffmpeg_psnr:
-        # libvmaf's psnr extractor logs all three planes when the pictures have chroma (integer_psnr.c, enable_chroma)
+    if opt.psnr or opt.psnr_chroma or opt.ffmpeg_psnr:
         opt_cols.append(("psnr_y", a["psnr_y"], L.FEAT_PSNR_Y))
+    if opt.psnr_chroma:
+        # libvmaf's psnr extractor logs all three planes unless enable_chroma=false (integer_psnr.c) -- which is what
+        # FFmpeg's `psnr=1` sets; the chroma columns are therefore opt-in
         opt_cols.append(("psnr_cb", a["psnr_cb"], L.FEAT_PSNR_UV))
         opt_cols.append(("psnr_cr", a["psnr_cr"], L.FEAT_PSNR_UV))
     if opt.float_motion and not is_f:
@@ -643,9 +649,9 @@ def build_frames(rows, model: VmafModel, opt: EngineOptions, device: int | None,
             m[f"{pre}motion"] = motion[i]
         for s in range(4):
             m[f"{pre}vif_scale{s}{vs}"] = vif[s]
-        if r["valid"] & L.FEAT_PSNR_Y and (opt.psnr or opt.ffmpeg_psnr):
+        if r["valid"] & L.FEAT_PSNR_Y and (opt.psnr or opt.psnr_chroma or opt.ffmpeg_psnr):
             m["psnr_y"] = r["psnr"][0]
-            if r["valid"] & L.FEAT_PSNR_UV:
+            if opt.psnr_chroma and r["valid"] & L.FEAT_PSNR_UV:
                 m["psnr_cb"], m["psnr_cr"] = r["psnr"][1], r["psnr"][2]
         if r["valid"] & L.FEAT_FLOAT_SSIM:
             m["float_ssim"] = r["float_ssim"]

@@ -173,12 +173,16 @@ class ChromaClip(Clip):
             p[...] = (i * 3) % 251
 
 
-def test_psnr_logs_all_three_planes_and_feature_motion_adds_the_float_extractor(fake):
-    """libvmaf `psnr=1` (app/vmaf_analyzer.py:385) logs psnr_y, psnr_cb, psnr_cr for pictures with chroma (the CSV export
-    of results_tab.py:3009-3026 takes its header from these keys); `feature=name=motion` (:388-402) adds the float
-    motion extractor's `motion` / `motion2` next to the integer model's features."""
+def test_psnr_columns_and_feature_motion_adds_the_float_extractor(fake):
+    """`psnr=1` (app/vmaf_analyzer.py:385) reaches libvmaf through FFmpeg's filter as the psnr extractor with
+    enable_chroma=false: psnr_y only; the extractor's own default (psnr_chroma) adds psnr_cb /
+    psnr_cr for pictures with chroma (the CSV export of results_tab.py:3009-3026 takes its header from these keys).
+    `feature=name=motion` (:388-402) adds the float motion extractor's `motion` / `motion2` next to the integer model's."""
     model = M.resolve_model("vmaf_v0.6.1")
-    res = engine.analyze(ChromaClip(12), model, _opt(psnr=True, float_motion=True))
+    plain = engine.analyze(ChromaClip(4), model, _opt(psnr=True))
+    assert "psnr_y" in plain["frames"][0]["metrics"] and "psnr_cb" not in plain["frames"][0]["metrics"]
+    fake.instances.clear()
+    res = engine.analyze(ChromaClip(12), model, _opt(psnr_chroma=True, float_motion=True))
     m = res["frames"][5]["metrics"]
     assert {"psnr_y", "psnr_cb", "psnr_cr", "motion", "motion2", "integer_motion", "integer_motion2", "vmaf"} <= set(m)
     fm = [fr["metrics"]["motion"] for fr in res["frames"]]
@@ -187,7 +191,7 @@ def test_psnr_logs_all_three_planes_and_feature_motion_adds_the_float_extractor(
     assert set(res["pooled_metrics"]) >= {"psnr_cb", "psnr_cr", "motion2"}
     # luma-only pictures: no chroma PSNR, as libvmaf for gray input
     fake.instances.clear()
-    res = engine.analyze(Clip(4), model, _opt(psnr=True))
+    res = engine.analyze(Clip(4), model, _opt(psnr_chroma=True))
     assert "psnr_y" in res["frames"][0]["metrics"] and "psnr_cb" not in res["frames"][0]["metrics"]
 
 

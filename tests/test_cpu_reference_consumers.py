@@ -56,7 +56,7 @@ def ref_module(monkeypatch):
         sys.modules.pop(k, None)
 
 
-def _engine_log(n=5, chroma=True):
+def _engine_log(n=5, chroma=False):
     """A log as engine.analyze builds it, from hand-made feature rows (no GPU needed): integer model + psnr=1 + ssim=1."""
     from pqa2_b200 import _lib as L
     from pqa2_b200 import engine, model as M
@@ -72,7 +72,7 @@ def _engine_log(n=5, chroma=True):
     a["float_ssim"] = rng.uniform(0.9, 1.0, n)
     rows.present[:] = True
     model = M.resolve_model("vmaf_v0.6.1")
-    opt = engine.EngineOptions(psnr=True, ssim=True, svr_on_device=False)
+    opt = engine.EngineOptions(psnr=True, psnr_chroma=chroma, ssim=True, svr_on_device=False)
     pooled_out = {}
     frames = engine.build_frames(rows, model, opt, None, pooled_out)
     return frames, pooled_out["pooled"]
@@ -108,9 +108,12 @@ def test_reference_parser_reads_our_log_and_stats_files(ref_module, tmp_path):
 
 def test_csv_export_header_matches_libvmaf_with_psnr_and_ssim(ref_module, tmp_path):
     """results_tab.py:3009-3026: header = 'Frame Number' + sorted(first frame's metric keys).  With `psnr=1:ssim=1`
-    libvmaf logs psnr_y, psnr_cb, psnr_cr and float_ssim next to the model's features; so must this engine."""
+    (FFmpeg maps psnr=1 to the psnr extractor with enable_chroma=false) libvmaf logs psnr_y and float_ssim next to the
+    model's features; so must this engine.  The extractor's chroma columns appear with EngineOptions.psnr_chroma."""
     from pqa2_b200 import report
     frames, pooled = _engine_log()
+    assert "psnr_cb" not in frames[0]["metrics"]
+    assert {"psnr_cb", "psnr_cr"} <= set(_engine_log(chroma=True)[0][0]["metrics"])
     jp = str(tmp_path / "T_vmaf.json")
     report.write_libvmaf_json(jp, frames, pooled, 100.0)
     raw = json.load(open(jp))
@@ -119,7 +122,7 @@ def test_csv_export_header_matches_libvmaf_with_psnr_and_ssim(ref_module, tmp_pa
     available = sorted(list(first.get("metrics", {}).keys()))
     want = sorted(["integer_adm2", "integer_adm_scale0", "integer_adm_scale1", "integer_adm_scale2", "integer_adm_scale3",
                    "integer_motion", "integer_motion2", "integer_vif_scale0", "integer_vif_scale1", "integer_vif_scale2",
-                   "integer_vif_scale3", "psnr_y", "psnr_cb", "psnr_cr", "float_ssim", "vmaf"])
+                   "integer_vif_scale3", "psnr_y", "float_ssim", "vmaf"])
     assert available == want
     for fr in raw["frames"]:
         for k in available:
