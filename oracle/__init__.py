@@ -25,6 +25,7 @@ _lib = None
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (idempotent)."""
     srcs = [os.path.join(_HERE, f) for f in ("vmaf_oracle.c", "vmaf_float_oracle.c", "Makefile")]
+    srcs.append(os.path.join(_HERE, "..", "include", "libvmaf_spec.h"))      # the constants both sides share
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH

@@ -13,6 +13,7 @@
  * written from the published algorithm.  The GPU kernels are held to it within the north star's
  * float tolerance (1e-4 per-frame VMAF, 1e-5 pooled), not bit-exactly.
  */
+#include "../include/libvmaf_spec.h"
 #include <math.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -41,13 +42,10 @@ ORC_API void orc_f_picture_copy(const void *src, int bpc, int w, int h, ptrdiff_
 }
 
 /* ============================== float VIF ============================================== */
-static const float vif_f17[17] = { 0.00745626912f, 0.0142655009f, 0.0250313189f, 0.0402820669f, 0.0594526194f,
-    0.0804751068f, 0.0999041125f, 0.113746084f, 0.118773937f, 0.113746084f, 0.0999041125f, 0.0804751068f,
-    0.0594526194f, 0.0402820669f, 0.0250313189f, 0.0142655009f, 0.00745626912f };
-static const float vif_f9[9] = { 0.0189780835f, 0.0558981746f, 0.120920904f, 0.192116052f, 0.224173605f,
-    0.192116052f, 0.120920904f, 0.0558981746f, 0.0189780835f };
-static const float vif_f5[5] = { 0.054488685f, 0.244201347f, 0.402619958f, 0.244201347f, 0.054488685f };
-static const float vif_f3[3] = { 0.166378498f, 0.667243004f, 0.166378498f };
+static const float vif_f17[17] = { SPEC_VIF_F32_17 };
+static const float vif_f9[9] = { SPEC_VIF_F32_9 };
+static const float vif_f5[5] = { SPEC_VIF_F32_5 };
+static const float vif_f3[3] = { SPEC_VIF_F32_3 };
 static const float *const vif_ftab[4] = { vif_f17, vif_f9, vif_f5, vif_f3 };
 static const int vif_fw[4] = { 17, 9, 5, 3 };
 
@@ -71,8 +69,7 @@ static void vif_filter1d(const float *f, int fw, const float *src, float *dst, f
 }
 
 /* vif_tools.c log2f_approx() (VIF_OPT_FAST_LOG2): exponent + degree-8 polynomial of the mantissa */
-static const float log2_poly[9] = { -0.012671635276421f, 0.064841182402670f, -0.157048836463065f,
-    0.257167726303123f, -0.353800560300520f, 0.480131410397451f, -0.721314327952201f, 1.442694803896991f, 0.0f };
+static const float log2_poly[9] = { SPEC_LOG2_POLY };
 ORC_API float orc_f_log2_approx(float x)
 {
     uint32_t u;
@@ -155,7 +152,7 @@ ORC_API int orc_f_vif(const float *ref, const float *dis, int w, int h, double e
 }
 
 /* ============================== float motion =========================================== */
-static const float motion_f5[5] = { 0.054488685f, 0.244201342f, 0.402619947f, 0.244201342f, 0.054488685f };
+static const float motion_f5[5] = { SPEC_MOTION_F32_5 };
 
 ORC_API void orc_f_motion_blur(const float *src, int w, int h, float *dst)
 {
@@ -188,8 +185,8 @@ ORC_API double orc_f_motion_sad(const float *a, const float *b, int w, int h)
 }
 
 /* ============================== float ADM ============================================== */
-static const float dwt_lo[4] = { 0.482962913144690f, 0.836516303737469f, 0.224143868041857f, -0.129409522550921f };
-static const float dwt_hi[4] = { -0.129409522550921f, -0.224143868041857f, 0.836516303737469f, -0.482962913144690f };
+static const float dwt_lo[4] = { SPEC_DWT_LO_F32 };
+static const float dwt_hi[4] = { SPEC_DWT_HI_F32 };
 
 typedef struct { float *a, *v, *h, *d; } fbands;
 
@@ -335,10 +332,8 @@ ORC_API int orc_f_adm(const float *ref, const float *dis, int w, int h, double e
 }
 
 /* ============================== SSIM / MS-SSIM (iqa) =================================== */
-static const float g_gauss11[11] = { 0.001028f, 0.007599f, 0.036001f, 0.109361f, 0.213006f, 0.266012f, 0.213006f,
-                                     0.109361f, 0.036001f, 0.007599f, 0.001028f };
-static const float g_lpf9[9] = { 0.026727f, -0.016828f, -0.078201f, 0.266846f, 0.602914f, 0.266846f, -0.078201f,
-                                 -0.016828f, 0.026727f };
+static const float g_gauss11[11] = { SPEC_SSIM_GAUSS11 };
+static const float g_lpf9[9] = { SPEC_MS_SSIM_LPF9 };
 
 static inline int sym(int i, int n)            /* KBND_SYMMETRIC: -1 -> 0 ; n -> n-1 */
 {
@@ -412,7 +407,7 @@ static void gauss_valid(const float *img, int w, int h, float *dst)
 /* _iqa_ssim(): sums of the ssim, l, c, s maps over the valid region.  sums[4] = ssim, l, c, s */
 static void ssim_maps(const float *ref, const float *cmp, int w, int h, double sums[4], int *count)
 {
-    const float C1 = (0.01f * 255.0f) * (0.01f * 255.0f), C2 = (0.03f * 255.0f) * (0.03f * 255.0f), C3 = C2 / 2.0f;
+    const float C1 = (SPEC_SSIM_K1 * 255.0f) * (SPEC_SSIM_K1 * 255.0f), C2 = (SPEC_SSIM_K2 * 255.0f) * (SPEC_SSIM_K2 * 255.0f), C3 = C2 / 2.0f;
     const int vw = w - 10, vh = h - 10;
     const size_t n = (size_t)w * h, vn = (size_t)vw * vh;
     float *t = malloc(4 * n), *mu1 = malloc(4 * vn), *mu2 = malloc(4 * vn), *s1 = malloc(4 * vn), *s2 = malloc(4 * vn),
@@ -462,7 +457,7 @@ ORC_API double orc_f_ssim(const float *ref, const float *cmp, int w, int h)
 ORC_API double orc_f_ms_ssim(const float *ref, const float *cmp, int w, int h, double *lcs)
 {
     static const double alphas[5] = { 0.0, 0.0, 0.0, 0.0, 0.1333 };
-    static const double betas[5] = { 0.0448, 0.2856, 0.3001, 0.2363, 0.1333 };
+    static const double betas[5] = { SPEC_MS_SSIM_EXPONENTS };
     float *r = malloc(4 * (size_t)w * h), *c = malloc(4 * (size_t)w * h);
     memcpy(r, ref, 4 * (size_t)w * h); memcpy(c, cmp, 4 * (size_t)w * h);
     double score = 1.0;

@@ -22,6 +22,7 @@
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off: no FMA contraction, so the few
  * float/double steps evaluate exactly as written).
  */
+#include "../include/libvmaf_spec.h"
 #include <math.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -48,7 +49,7 @@ static inline uint32_t px(const void *p, int bpc, ptrdiff_t stride, int i, int j
  * 5-tap Q16 blur, vertical then horizontal, asymmetric mirror borders
  * (idx < 0 -> -idx ; idx >= n -> 2n - idx - 1); SAD against the previous blurred frame.
  * ======================================================================================== */
-static const uint16_t motion_filter[5] = { 3571, 16004, 26386, 16004, 3571 };
+static const uint16_t motion_filter[5] = { SPEC_MOTION_Q16_5 };
 
 static inline int mirror_asym(int i, int n)
 {
@@ -96,12 +97,7 @@ ORC_API double orc_motion_score(uint64_t sad, int w, int h)
 /* ==========================================================================================
  * Integer VIF (libvmaf integer_vif.c).
  * ======================================================================================== */
-static const uint16_t vif_filter[4][17] = {
-    { 489, 935, 1640, 2640, 3896, 5274, 6547, 7455, 7784, 7455, 6547, 5274, 3896, 2640, 1640, 935, 489 },
-    { 1244, 3663, 7925, 12590, 14692, 12590, 7925, 3663, 1244 },
-    { 3571, 16004, 26386, 16004, 3571 },
-    { 10904, 43728, 10904 }
-};
+static const uint16_t vif_filter[4][17] = { { SPEC_VIF_Q16_17 }, { SPEC_VIF_Q16_9 }, { SPEC_VIF_Q16_5 }, { SPEC_VIF_Q16_3 } };
 static const int vif_filter_width[4] = { 17, 9, 5, 3 };
 
 static uint16_t vif_log2_table[65536];
@@ -331,11 +327,11 @@ ORC_API int orc_vif(const void *ref, const void *dis, int bpc, int w, int h, ptr
 /* ==========================================================================================
  * Integer ADM (libvmaf integer_adm.c).
  * ======================================================================================== */
-static const int32_t dwt_lo[4] = { 15826, 27411, 7345, -4240 };
-static const int32_t dwt_hi[4] = { -4240, -7345, 27411, -15826 };
-static const int32_t dwt_lo_sum = 46342;
+static const int32_t dwt_lo[4] = { SPEC_DWT_LO_Q15 };
+static const int32_t dwt_hi[4] = { SPEC_DWT_HI_Q15 };
+static const int32_t dwt_lo_sum = SPEC_DWT_LO_SUM_Q15;
 
-#define ADM_BORDER_FACTOR 0.1
+#define ADM_BORDER_FACTOR SPEC_ADM_BORDER_FACTOR
 
 static int32_t adm_div_lookup[65537];
 static int adm_div_ready = 0;
@@ -353,13 +349,8 @@ static void adm_div_init(void)
 
 /* Watson DWT quantisation step (float evaluation as in libvmaf adm_tools.h dwt_quant_step). */
 struct dwt_model_params { float a, k, f0, g[4]; };
-static const struct dwt_model_params dwt_7_9_Y = { 0.495f, 0.466f, 0.401f, { 1.501f, 1.0f, 0.534f, 1.0f } };
-static const float dwt_7_9_amp[4][4] = {
-    { 0.62171f, 0.67234f, 0.72709f, 0.67234f },
-    { 0.34537f, 0.41317f, 0.49428f, 0.41317f },
-    { 0.18004f, 0.22727f, 0.28688f, 0.22727f },
-    { 0.091401f, 0.11792f, 0.15214f, 0.11792f },
-};
+static const struct dwt_model_params dwt_7_9_Y = { SPEC_DWT79_A, SPEC_DWT79_K, SPEC_DWT79_F0, { SPEC_DWT79_G } };
+static const float dwt_7_9_amp[4][4] = { SPEC_DWT79_AMP };
 static float dwt_quant_step(int lambda, int theta, double view_dist, int display_h)
 {
     float r = view_dist * display_h * M_PI / 180.0;
@@ -426,8 +417,8 @@ static void adm_dwt_s123(const int32_t *src, int w, int h, int scale, bands_t *d
 {
     static const int64_t rnd_v[3] = { 0, 32768, 32768 };
     static const int64_t rnd_h[3] = { 16384, 32768, 16384 };
-    static const int sh_v[3] = { 0, 16, 16 };
-    static const int sh_h[3] = { 15, 16, 15 };
+    static const int sh_v[3] = { SPEC_ADM_DWT_SH_V };
+    static const int sh_h[3] = { SPEC_ADM_DWT_SH_H };
     const int ow = (w + 1) / 2, oh = (h + 1) / 2, s = scale - 1;
     int32_t *tlo = malloc(sizeof(int32_t) * w), *thi = malloc(sizeof(int32_t) * w);
     for (int i = 0; i < oh; ++i) {
@@ -528,7 +519,8 @@ static void adm_scale(const bands_t *ref, const bands_t *dis, int w, int h, int 
     uint32_t i_rf[3];
     if (scale == 0) {
         if (fabs(view_dist * display_h - 3.0 * 1080) < 1.0e-8) {
-            i_rf[0] = 36453; i_rf[1] = 36453; i_rf[2] = 49417;
+            static const uint32_t s0_rf[3] = { SPEC_ADM_S0_RF };
+            i_rf[0] = s0_rf[0]; i_rf[1] = s0_rf[1]; i_rf[2] = s0_rf[2];
         } else {
             i_rf[0] = (uint16_t)(rf[0] * pow(2, 21));
             i_rf[1] = (uint16_t)(rf[1] * pow(2, 21));
@@ -554,8 +546,8 @@ static void adm_scale(const bands_t *ref, const bands_t *dis, int w, int h, int 
     const int32_t *TB[3] = { dis->h, dis->v, dis->d };
 
     /* scale-0 csf constants */
-    static const int s0_shift[3] = { 15, 15, 17 };
-    static const int32_t s0_add[3] = { 16384, 16384, 65536 };
+    static const int s0_shift[3] = { SPEC_ADM_S0_RF_SHIFT };
+    static const int32_t s0_add[3] = { SPEC_ADM_S0_RF_ROUND };
 
     for (int i = gt; i < gb; ++i)
         for (int j = gl; j < gr; ++j) {
@@ -570,11 +562,11 @@ static void adm_scale(const bands_t *ref, const bands_t *dis, int w, int h, int 
                     int32_t dv = (int32_t)i_rf[b] * a[b];
                     int16_t ca = (int16_t)((dv + s0_add[b]) >> s0_shift[b]);
                     CA[b][p] = ca;
-                    CF[b][p] = (int16_t)(((4369 * abs((int32_t)ca)) + 2048) >> 12);
+                    CF[b][p] = (int16_t)(((SPEC_ADM_ONE_BY_30_Q16 * abs((int32_t)ca)) + 2048) >> 12);
                 } else {
                     int32_t ca = (int32_t)((((int64_t)i_rf[b] * (int64_t)a[b]) + (1ll << 27)) >> 28);
                     CA[b][p] = ca;
-                    CF[b][p] = (int32_t)((((int64_t)143165577 * abs(ca)) + (1ll << 31)) >> 32);
+                    CF[b][p] = (int32_t)((((int64_t)SPEC_ADM_ONE_BY_30_Q32 * abs(ca)) + (1ll << 31)) >> 32);
                 }
             }
         }
@@ -613,9 +605,9 @@ static void adm_scale(const bands_t *ref, const bands_t *dis, int w, int h, int 
                         size_t q = (size_t)ii * w + jj;
                         if (di == 0 && dj == 0) {
                             if (scale == 0)
-                                sum += (int16_t)(((8738 * abs(CA[b][q])) + 2048) >> 12);
+                                sum += (int16_t)(((SPEC_ADM_ONE_BY_15_Q16 * abs(CA[b][q])) + 2048) >> 12);
                             else
-                                sum += (int32_t)((((int64_t)286331153 * abs(CA[b][q])) + (1ll << 31)) >> 32);
+                                sum += (int32_t)((((int64_t)SPEC_ADM_ONE_BY_15_Q32 * abs(CA[b][q])) + (1ll << 31)) >> 32);
                         } else {
                             sum += CF[b][q];
                         }
@@ -820,7 +812,7 @@ ORC_API double orc_ffssim_plane(const void *a, const void *b, int bpc, int w, in
                     s1 += d[0]; s2 += d[1]; ss += d[2]; s12 += d[3];
                 }
             if (bpc == 8) {
-                const int c1 = 416, c2 = 235963;
+                const int c1 = SPEC_FFSSIM_C1, c2 = SPEC_FFSSIM_C2;
                 int fs1 = (int)s1, fs2 = (int)s2, fss = (int)ss, fs12 = (int)s12;
                 int vars = fss * 64 - fs1 * fs1 - fs2 * fs2;
                 int covar = fs12 * 64 - fs1 * fs2;

@@ -14,6 +14,7 @@
 // threshold) = 136x38 staged input samples per picture, prefetched into registers one tile ahead.
 #include "bv_common.cuh"
 #include "../../include/b200vmaf.h"
+#include "../../include/libvmaf_spec.h"
 #include <math.h>
 #include <type_traits>
 
@@ -26,9 +27,9 @@ constexpr int AN_P = AN_C;                               // shared-memory pitch 
 constexpr int AN_G = AN_C / 4;                           // 4-sample groups per staged row
 constexpr int A_RING = 2 * AP_W + 2 * AT_H;              // halo-only positions
 
-__constant__ int c_dwt_lo[4] = { 15826, 27411, 7345, -4240 };
-__constant__ int c_dwt_hi[4] = { -4240, -7345, 27411, -15826 };
-constexpr int DWT_LO_SUM = 46342;
+__constant__ int c_dwt_lo[4] = { SPEC_DWT_LO_Q15 };
+__constant__ int c_dwt_hi[4] = { SPEC_DWT_HI_Q15 };
+constexpr int DWT_LO_SUM = SPEC_DWT_LO_SUM_Q15;
 
 struct AdmArgs {
     BvPlane ref, dis;                // input of this scale (picture or previous band_a)
@@ -122,13 +123,13 @@ __device__ __forceinline__ void adm_decouple_csf(const int (&o)[3], const int (&
             const int sh = b == 2 ? 17 : 15;
             const int dv = (int)(a.sp.rf[b] * (unsigned)ad);
             ca = (short)((dv + (1 << (sh - 1))) >> sh);
-            cf_acc += (unsigned)(int)(short)((4369 * abs(ca) + 2048) >> 12);
-            cc_acc += (unsigned)(int)(short)((8738 * abs(ca) + 2048) >> 12);
+            cf_acc += (unsigned)(int)(short)((SPEC_ADM_ONE_BY_30_Q16 * abs(ca) + 2048) >> 12);
+            cc_acc += (unsigned)(int)(short)((SPEC_ADM_ONE_BY_15_Q16 * abs(ca) + 2048) >> 12);
             x = (int)((unsigned)rst * a.sp.rf[b]);
         } else {
             ca = (int)(((long long)a.sp.rf[b] * (long long)ad + (1ll << 27)) >> 28);
-            cf_acc += (unsigned)(int)((143165577ll * abs(ca) + (1ll << 31)) >> 32);
-            cc_acc += (unsigned)(int)((286331153ll * abs(ca) + (1ll << 31)) >> 32);
+            cf_acc += (unsigned)(int)((SPEC_ADM_ONE_BY_30_Q32 * abs(ca) + (1ll << 31)) >> 32);
+            cc_acc += (unsigned)(int)((SPEC_ADM_ONE_BY_15_Q32 * abs(ca) + (1ll << 31)) >> 32);
             x = (int)(((long long)rst * (long long)a.sp.rf[b] + (1ll << 27)) >> 28);
         }
         xabs[b] = abs(x);
@@ -488,11 +489,9 @@ float dwt_quant_step(int lambda, int theta, double view_dist, int display_h)
 {
     // Watson et al. DWT quantisation model, evaluated the way libvmaf's adm_tools.h does (float
     // temporaries around double libm calls).
-    static const float amp[4][4] = {
-        { 0.62171f, 0.67234f, 0.72709f, 0.67234f }, { 0.34537f, 0.41317f, 0.49428f, 0.41317f },
-        { 0.18004f, 0.22727f, 0.28688f, 0.22727f }, { 0.091401f, 0.11792f, 0.15214f, 0.11792f } };
-    static const float g[4] = { 1.501f, 1.0f, 0.534f, 1.0f };
-    const float a = 0.495f, k = 0.466f, f0 = 0.401f;
+    static const float amp[4][4] = { SPEC_DWT79_AMP };
+    static const float g[4] = { SPEC_DWT79_G };
+    const float a = SPEC_DWT79_A, k = SPEC_DWT79_K, f0 = SPEC_DWT79_F0;
     float r = view_dist * display_h * M_PI / 180.0;
     float temp = log10(pow(2.0, lambda + 1) * f0 * g[theta] / r);
     float Q = 2.0 * a * pow(10.0, k * temp * temp) / amp[lambda][theta];
@@ -517,13 +516,14 @@ void bv_adm_make_params(int w, int h, double view_dist, int display_h, BvAdmScal
         p.in_w = cw; p.in_h = ch;
         cw = (cw + 1) / 2; ch = (ch + 1) / 2;
         p.w = cw; p.h = ch;
-        p.left = (int)(cw * 0.1 - 0.5); p.top = (int)(ch * 0.1 - 0.5);
+        p.left = (int)(cw * SPEC_ADM_BORDER_FACTOR - 0.5); p.top = (int)(ch * SPEC_ADM_BORDER_FACTOR - 0.5);
         p.right = cw - p.left; p.bottom = ch - p.top;
         float rf[3];
         bv_adm_rfactor(s, view_dist, display_h, rf);
         if (s == 0) {
             if (fabs(view_dist * display_h - 3.0 * 1080) < 1.0e-8) {
-                p.rf[0] = 36453; p.rf[1] = 36453; p.rf[2] = 49417;
+                static const unsigned s0_rf[3] = { SPEC_ADM_S0_RF };
+                p.rf[0] = s0_rf[0]; p.rf[1] = s0_rf[1]; p.rf[2] = s0_rf[2];
             } else {
                 p.rf[0] = (uint16_t)(rf[0] * pow(2, 21)); p.rf[1] = (uint16_t)(rf[1] * pow(2, 21));
                 p.rf[2] = (uint16_t)(rf[2] * pow(2, 23));

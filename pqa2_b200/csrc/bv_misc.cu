@@ -8,6 +8,7 @@
 // (SURVEY.md Appendix A.6), one CTA per frame, one thread per support vector, fixed-order tree sum.
 #include "bv_common.cuh"
 #include "../../include/b200vmaf.h"
+#include "../../include/libvmaf_spec.h"
 
 namespace {
 
@@ -153,7 +154,7 @@ ffssim_kernel(BvBatch batch, BvPlane ref, BvPlane dis, int bpc, int w, int h, do
                     ss += s_blk[r + dy][c + dx][2]; s12 += s_blk[r + dy][c + dx][3];
                 }
             S c1, c2;
-            if (sizeof(T) == 1) { c1 = 416; c2 = 235963; }
+            if (sizeof(T) == 1) { c1 = SPEC_FFSSIM_C1; c2 = SPEC_FFSSIM_C2; }
             else {
                 const int maxv = (1 << bpc) - 1;
                 c1 = (S)(long long)(.01 * .01 * maxv * maxv * 64 + .5);

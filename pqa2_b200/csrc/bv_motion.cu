@@ -6,6 +6,7 @@
 // reads W*H*bytes (luma) + writes W*H*2 (blur) + SAD reads 2*W*H*2.
 #include "bv_common.cuh"
 #include "../../include/b200vmaf.h"
+#include "../../include/libvmaf_spec.h"
 
 namespace {
 
@@ -16,7 +17,7 @@ constexpr int MB_IN_W = MB_TW + 8, MB_IN_H = MB_TH + 2 * MB_R, MB_G = MB_IN_W / 
 constexpr int MB_P = MB_IN_W;            // u16 pitch of the staged tile: 8-byte rows (one 8-byte store per group; only read column-per-lane)
 constexpr int MB_VP = MB_IN_W + 1;       // odd u32 pitch of the vertical-pass plane
 
-__constant__ unsigned c_motion_filter[5] = { 3571, 16004, 26386, 16004, 3571 };
+__constant__ unsigned c_motion_filter[5] = { SPEC_MOTION_Q16_5 };
 
 template <typename T>
 __global__ void __launch_bounds__(256)
