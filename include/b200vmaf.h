@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BV_ABI_VERSION 1
+#define BV_ABI_VERSION 2   /* 2: bv_host_register / bv_host_unregister, bv_opts.fast_float (took one reserved word) */
 
 /* feature groups (bv_create features_mask) */
 #define BV_FEAT_MOTION      0x001u  /* integer_motion / integer_motion2           (libvmaf integer_motion.c) */

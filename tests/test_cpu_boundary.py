@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in b200vmaf.h but not exported"
     assert set(L.EXPORTS) <= declared
-    assert lib.bv_abi_version() == 1
+    assert lib.bv_abi_version() == 2
     assert lib.bv_sizeof_frame_features() == C.sizeof(L.BvFrameFeatures)
 
 
