@@ -152,3 +152,28 @@ def test_oracle_matches_fullsize_golden_1080p():
     v, a = oracle.vif(rp[0], dp[0], c["bpc"], c["egl"]), oracle.adm(rp[0], dp[0], c["bpc"], c["egl"])
     assert v["acc"].tolist() == c["vif_acc"] and a["cm"].tolist() == c["adm_cm"] and a["adm2"] == c["adm2"]
     assert [[int(x) for x in r] for r in a["den"]] == c["adm_den"] and oracle.sse(rp[0], dp[0], c["bpc"]) == c["sse_y"]
+
+
+@pytest.mark.parametrize("seed,w,h,bpc", [(3, 352, 288, 8), (8, 416, 240, 10), (5, 640, 360, 8)])
+def test_integer_and_float_restatements_agree(seed, w, h, bpc):
+    """Two differently built restatements of the same features -- fixed point with hard-coded tables, shifts and CSF integers
+    (integer_vif / integer_adm / integer_motion) against float formulas (vif / adm / motion) -- agree to a few 1e-4, as
+    libvmaf's own integer and float extractors do.  A wrong shift, table or CSF constant on either side (the M / L items of
+    SURVEY.md Appendix A, e.g. the scale-0 integers 36453 / 49417 or the ADM DWT shifts of scales 1-3) would show here as a
+    difference orders of magnitude larger; it does not replace a libvmaf log, it bounds what such a log could still move."""
+    rp, dp = synth.frame_pair(seed, 1, w, h, bpc, chroma=False)
+    pp, _ = synth.frame_pair(seed, 0, w, h, bpc, chroma=False)
+    i = oracle.integer_features(rp[0], dp[0], bpc)
+    f = oracle.float_features(rp[0], dp[0], bpc, prev_ref=pp[0])
+    assert abs(i["integer_adm2"] - f["adm2"]) < 5e-4
+    for s in range(4):
+        assert abs(i[f"integer_vif_scale{s}"] - f[f"vif_scale{s}"]) < 5e-4
+        assert abs(i[f"integer_adm_scale{s}"] - f[f"adm_scale{s}"]) < 3e-3
+    im = oracle.motion_score(oracle.motion_sad(oracle.motion_blur(rp[0], bpc), oracle.motion_blur(pp[0], bpc)), w, h)
+    assert im > 0.5 and abs(im - f["motion"]) < 1e-4
+    # through the (shared) SVR the two paths land within a few hundredths of a VMAF point
+    from pqa2_b200 import model as M
+    mi, mf = M.resolve_model("vmaf_v0.6.1"), M.resolve_model("vmaf_float_v0.6.1")
+    xi = np.array([[i["integer_adm2"], 0.0] + [i[f"integer_vif_scale{s}"] for s in range(4)]])
+    xf = np.array([[f["adm2"], 0.0] + [f[f"vif_scale{s}"] for s in range(4)]])
+    assert abs(mi.main.predict(xi)[0] - mf.main.predict(xf)[0]) < 0.05
