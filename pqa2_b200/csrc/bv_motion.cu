@@ -104,27 +104,14 @@ motion_sad_kernel(BvBatch batch, const uint16_t *__restrict__ blur, const uint16
     const size_t n8 = n_elems / 8;
     const uint4 *c4 = reinterpret_cast<const uint4 *>(cur);
     const uint4 *p4 = reinterpret_cast<const uint4 *>(prv);
-    // 4 x 2 independent 16-byte loads in flight per lane (a streaming read is bound by the bytes in flight; with one
-    // pair per iteration the launch reached 44 % of the HBM peak)
-    constexpr int U = 4;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += stride * U) {
-        uint4 a[U], b[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const size_t i = i0 + stride * u;
-            if (i < n8) { a[u] = __ldg(c4 + i); b[u] = __ldg(p4 + i); }
-            else { a[u] = make_uint4(0, 0, 0, 0); b[u] = a[u]; }
-        }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 a = __ldg(c4 + i), b = __ldg(p4 + i);
         unsigned s = 0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            // per-halfword absolute differences, summed (max 32 * 65535 fits easily)
-            s += __vsadu2(a[u].x, b[u].x);
-            s += __vsadu2(a[u].y, b[u].y);
-            s += __vsadu2(a[u].z, b[u].z);
-            s += __vsadu2(a[u].w, b[u].w);
-        }
+        // per-halfword absolute differences, summed (max 8 * 65535 fits easily)
+        s += __vsadu2(a.x, b.x);
+        s += __vsadu2(a.y, b.y);
+        s += __vsadu2(a.z, b.z);
+        s += __vsadu2(a.w, b.w);
         sad += s;
     }
     if (blockIdx.x == 0) {
