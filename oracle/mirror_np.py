@@ -303,3 +303,112 @@ def adm_dwt_scale0(luma: np.ndarray, bpc: int = 8) -> np.ndarray:
         cols = src[:, jx]                                 # [oh, ow, 4]
         out.append(to16((cols @ np.array(taps) + 32768) >> 16))
     return np.stack(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# float ADM (adm.c / adm_tools.c): DWT, decoupling, CSF, contrast masking -- whole-plane fp32 array code
+# ---------------------------------------------------------------------------------------------
+DWT_LO_F = np.array([0.482962913144690, 0.836516303737469, 0.224143868041857, -0.129409522550921], np.float32)
+DWT_HI_F = np.array([-0.129409522550921, -0.224143868041857, 0.836516303737469, -0.482962913144690], np.float32)
+
+
+def rfactor(scale: int, view_dist: float = 3.0, display_h: int = 1080) -> np.ndarray:
+    """1 / Q(scale, theta) of Watson's 9/7 DWT quantisation model, theta = 1 for h and v, 2 for d; float temporaries
+    around double libm calls as adm_tools.h writes them."""
+    f32 = np.float32
+    amp = [[0.62171, 0.67234, 0.72709, 0.67234], [0.34537, 0.41317, 0.49428, 0.41317],
+           [0.18004, 0.22727, 0.28688, 0.22727], [0.091401, 0.11792, 0.15214, 0.11792]]
+    g = [1.501, 1.0, 0.534, 1.0]
+    out = []
+    for theta in (1, 1, 2):
+        r = f32(view_dist * display_h * np.pi / 180.0)
+        temp = f32(np.log10(2.0 ** (scale + 1) * float(f32(0.401)) * float(f32(g[theta])) / float(r)))
+        q = f32(2.0 * float(f32(0.495)) * 10.0 ** (float(f32(0.466)) * float(temp) * float(temp)) / float(f32(amp[scale][theta])))
+        out.append(f32(1.0) / q)
+    return np.array(out, np.float32)
+
+
+def _dwt_f32(p: np.ndarray):
+    """one level of the float db2 decomposition; accumulation order lo/hi[0]*s0 + [1]*s1 + [2]*s2 + [3]*s3, fp32 each step"""
+    h, w = p.shape
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    iy, jx = _dwt_index(oh, h), _dwt_index(ow, w)
+    f32 = np.float32
+
+    def comb(vals, taps):                                  # vals: [..., 4] along the last axis
+        acc = np.zeros(vals.shape[:-1], f32)
+        for k in range(4):
+            acc = (acc + (vals[..., k] * taps[k]).astype(f32)).astype(f32)
+        return acc
+
+    rows = np.moveaxis(p[iy], 1, -1)                       # [oh, w, 4]
+    lo, hi = comb(rows, DWT_LO_F), comb(rows, DWT_HI_F)
+    a, v = comb(lo[:, jx], DWT_LO_F), comb(lo[:, jx], DWT_HI_F)
+    hb, d = comb(hi[:, jx], DWT_LO_F), comb(hi[:, jx], DWT_HI_F)
+    return a, v, hb, d
+
+
+def adm_float(ref_f: np.ndarray, dis_f: np.ndarray, egl: float = 100.0, rf_of=None):
+    """-> (num_scale[4], den_scale[4], adm2).  ref_f / dis_f: float32 luma - 128.  `rf_of(scale)` supplies the CSF factors
+    (default: rfactor())."""
+    f32 = np.float32
+    x, y = ref_f.astype(f32), dis_f.astype(f32)
+    H0, W0 = x.shape
+    cos2 = f32(np.cos(np.pi / 180.0) * np.cos(np.pi / 180.0))
+    eps, by30, by15 = f32(1e-30), f32(0.0333333351), f32(0.0666666701)
+    nums, dens = np.zeros(4), np.zeros(4)
+    for scale in range(4):
+        ra, rv, rh, rd = _dwt_f32(x)
+        da, dv, dh, dd = _dwt_f32(y)
+        x, y = ra, da
+        h, w = ra.shape
+        rf = (rf_of or rfactor)(scale).astype(f32)
+        O, T = [rh, rv, rd], [dh, dv, dd]
+        ot = ((rh * dh).astype(f32) + (rv * dv).astype(f32)).astype(f32)
+        om = ((rh * rh).astype(f32) + (rv * rv).astype(f32)).astype(f32)
+        tm = ((dh * dh).astype(f32) + (dv * dv).astype(f32)).astype(f32)
+        flag = (ot >= 0) & ((ot * ot).astype(f32) >= ((cos2 * om).astype(f32) * tm).astype(f32))
+        R, CA, CF = [], [], []
+        for b in range(3):
+            o, t = O[b], T[b]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                k = np.clip((t / (o + eps).astype(f32)).astype(f32), f32(0), f32(1))
+            rst = (k * o).astype(f32)
+            v = rst.astype(np.float64) * egl
+            t64 = t.astype(np.float64)
+            lim = np.where(rst > 0, np.minimum(v, t64), np.where(rst < 0, np.maximum(v, t64), rst.astype(np.float64)))
+            rst = np.where(flag, lim, rst.astype(np.float64)).astype(f32)
+            ca = (rf[b] * (t - rst).astype(f32)).astype(f32)
+            R.append(rst); CA.append(ca); CF.append((by30 * np.abs(ca)).astype(f32))
+        left, top = int(w * 0.1 - 0.5), int(h * 0.1 - 0.5)
+        right, bottom = w - left, h - top
+        ys, xs = slice(top, bottom), slice(left, right)
+        thr = np.zeros((bottom - top, right - left), f32)
+        for b in range(3):
+            s = np.zeros_like(thr)
+            cfp = _pad_mirror(_pad_mirror(CF[b], 1, 0), 1, 1)        # neighbours past the band edge fold back (small bands)
+            for di in (-1, 0, 1):
+                for dj in (-1, 0, 1):
+                    if di == 0 and dj == 0:
+                        term = (by15 * np.abs(CA[b][ys, xs])).astype(f32)
+                    else:
+                        term = cfp[top + 1 + di:bottom + 1 + di, left + 1 + dj:right + 1 + dj]
+                    s = (s + term).astype(f32)
+            thr = (thr + s).astype(f32)
+        area = f32(np.power(f32((bottom - top) * (right - left)) / f32(32.0), f32(1.0 / 3.0), dtype=f32))
+        ns = ds = f32(0)
+        for b in range(3):
+            xn = np.maximum((np.abs((R[b][ys, xs] * rf[b]).astype(f32)) - thr).astype(f32), f32(0))
+            cn = ((xn * xn).astype(f32) * xn).astype(f32)
+            vd = (np.abs(O[b][ys, xs]) * rf[b]).astype(f32)
+            cd = ((vd * vd).astype(f32) * vd).astype(f32)
+            # adm_tools.c order: a float sum per row, the rows added into another float
+            an = np.cumsum(np.cumsum(cn, axis=1, dtype=f32)[:, -1], dtype=f32)[-1]
+            ad = np.cumsum(np.cumsum(cd, axis=1, dtype=f32)[:, -1], dtype=f32)[-1]
+            ns = f32(ns + f32(np.power(an, f32(1.0 / 3.0), dtype=f32) + area))
+            ds = f32(ds + f32(np.power(ad, f32(1.0 / 3.0), dtype=f32) + area))
+        nums[scale], dens[scale] = float(ns), float(ds)
+    limit = 1e-10 * (W0 * H0) / (1920.0 * 1080.0)
+    num, den = nums.sum(), dens.sum()
+    num, den = (0.0 if num < limit else num), (0.0 if den < limit else den)
+    return nums, dens, (1.0 if den == 0.0 else num / den)

@@ -93,3 +93,27 @@ def test_integer_adm_scale0_wavelet_bands_agree(seed, w, h, bpc):
     assert got.shape == want.shape
     np.testing.assert_array_equal(got, want)
     assert np.abs(want[1:]).max() > 0                     # the detail bands are not trivially zero
+
+
+@pytest.mark.parametrize("seed,w,h,bpc,egl", [(3, 176, 144, 8, 100.0), (5, 322, 242, 8, 1.0), (8, 208, 120, 10, 100.0)])
+def test_float_adm_agrees(seed, w, h, bpc, egl):
+    """float ADM (DWT, decoupling with the 1-degree angle test and the gain limit, CSF, 3x3 contrast-masking threshold, cube
+    sums) as whole-plane fp32 array code against the C oracle's per-pixel loops."""
+    rp, dp = synth.frame_pair(seed, 1, w, h, bpc, chroma=False)
+    rf, df = oracle.picture_copy(rp[0], bpc, -128.0), oracle.picture_copy(dp[0], bpc, -128.0)
+    c = oracle.f_adm(rf, df, egl)
+    nums, dens, adm2 = MN.adm_float(rf, df, egl, rf_of=oracle.adm_rfactor)
+    np.testing.assert_allclose(c["num_scale"], nums, rtol=2e-6)
+    np.testing.assert_allclose(c["den_scale"], dens, rtol=2e-6)
+    assert abs(c["adm2"] - adm2) < 2e-6 and 0.3 < adm2 < 1.1
+
+
+def test_csf_factors_follow_the_watson_model():
+    """rfactor = 1 / Q(scale, theta): the mirror's evaluation, the oracle's, and the values SURVEY.md Appendix A.4 lists."""
+    listed = [(0.0173815, 0.0058907), (0.0319848, 0.0142991), (0.0433727, 0.0243969), (0.0456734, 0.0313127)]
+    for s in range(4):
+        a, b = MN.rfactor(s), oracle.adm_rfactor(s)
+        np.testing.assert_allclose(a, b, rtol=3e-7)
+        assert abs(a[0] - listed[s][0]) < 5e-7 and a[0] == a[1] and abs(a[2] - listed[s][1]) < 5e-7
+    # the integer path's hard-coded scale-0 factors (include/libvmaf_spec.h, tagged L) against the model
+    assert abs(36453 / 2.0 ** 21 - MN.rfactor(0)[0]) < 1e-6 and abs(49417 / 2.0 ** 23 - MN.rfactor(0)[2]) < 1e-6
