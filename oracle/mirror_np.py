@@ -412,3 +412,52 @@ def adm_float(ref_f: np.ndarray, dis_f: np.ndarray, egl: float = 100.0, rf_of=No
     num, den = nums.sum(), dens.sum()
     num, den = (0.0 if num < limit else num), (0.0 if den < limit else den)
     return nums, dens, (1.0 if den == 0.0 else num / den)
+
+
+# ---------------------------------------------------------------------------------------------
+# iqa MS-SSIM (ms_ssim.c): float64 throughout -- a tolerance check of the fp32 oracle, not a bit check
+# ---------------------------------------------------------------------------------------------
+GAUSS11 = np.array([0.001028, 0.007599, 0.036001, 0.109361, 0.213006, 0.266012, 0.213006, 0.109361, 0.036001, 0.007599,
+                    0.001028])
+LPF9 = np.array([0.026727, -0.016828, -0.078201, 0.266846, 0.602914, 0.266846, -0.078201, -0.016828, 0.026727])
+
+
+def _valid11(a: np.ndarray) -> np.ndarray:
+    h, w = a.shape
+    t = sum(a[:, k:w - 10 + k] * GAUSS11[k] for k in range(11))
+    return sum(t[k:h - 10 + k, :] * GAUSS11[k] for k in range(11))
+
+
+def _sym_index(n_out: int, n: int, step: int, off: int, taps: int) -> np.ndarray:
+    idx = step * np.arange(n_out)[:, None] + off + np.arange(taps)[None, :]
+    idx = np.where(idx < 0, -1 - idx, idx)
+    return np.where(idx >= n, 2 * n - idx - 1, idx)
+
+
+def _decimate2(a: np.ndarray) -> np.ndarray:
+    """9-tap low-pass along x then y, keep every second sample, symmetric borders (-1 -> 0, n -> n - 1)"""
+    h, w = a.shape
+    dw, dh = w // 2 + (w & 1), h // 2 + (h & 1)
+    t = a[:, _sym_index(dw, w, 2, -4, 9)] @ LPF9
+    return np.tensordot(t[_sym_index(dh, h, 2, -4, 9)], LPF9, axes=([1], [0]))
+
+
+def ms_ssim(ref0: np.ndarray, dis0: np.ndarray):
+    """-> (score, lcs[5, 3]).  ref0 / dis0: luma as float in [0, 255]."""
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    c3 = c2 / 2
+    expo = [0.0448, 0.2856, 0.3001, 0.2363, 0.1333]
+    r, c = ref0.astype(np.float64), dis0.astype(np.float64)
+    score, lcs = 1.0, np.zeros((5, 3))
+    for s in range(5):
+        if s:
+            r, c = _decimate2(r), _decimate2(c)
+        m1, m2 = _valid11(r), _valid11(c)
+        v1 = np.maximum(_valid11(r * r) - m1 * m1, 0)
+        v2 = np.maximum(_valid11(c * c) - m2 * m2, 0)
+        cv = _valid11(r * c) - m1 * m2
+        sr = np.sqrt(v1 * v2)
+        lcs[s] = [np.mean((2 * m1 * m2 + c1) / (m1 * m1 + m2 * m2 + c1)), np.mean((2 * sr + c2) / (v1 + v2 + c2)),
+                  np.mean((cv + c3) / (sr + c3))]
+        score *= (lcs[s, 0] ** (expo[4] if s == 4 else 0.0)) * lcs[s, 1] ** expo[s] * lcs[s, 2] ** expo[s]
+    return score, lcs

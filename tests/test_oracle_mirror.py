@@ -117,3 +117,17 @@ def test_csf_factors_follow_the_watson_model():
         assert abs(a[0] - listed[s][0]) < 5e-7 and a[0] == a[1] and abs(a[2] - listed[s][1]) < 5e-7
     # the integer path's hard-coded scale-0 factors (include/libvmaf_spec.h, tagged L) against the model
     assert abs(36453 / 2.0 ** 21 - MN.rfactor(0)[0]) < 1e-6 and abs(49417 / 2.0 ** 23 - MN.rfactor(0)[2]) < 1e-6
+
+
+@pytest.mark.parametrize("seed,w,h,bpc", [(4, 352, 288, 8), (8, 416, 240, 10), (4, 335, 253, 8)])
+def test_ms_ssim_agrees_with_a_float64_restatement(seed, w, h, bpc):
+    """float_ms_ssim: 5 scales, valid 11-tap Gaussian moments, 9-tap low-pass decimation with symmetric borders, per-scale
+    means of l, c, s, exponents -- the fp32 oracle against the same pipeline in float64.  The fp32 variance subtraction costs
+    a few 1e-6 on the c and s means of the finest scale and less than 1e-5 on the score."""
+    rp, dp = synth.frame_pair(seed, 0, w, h, bpc, chroma=False)
+    r0, d0 = oracle.picture_copy(rp[0], bpc, 0.0), oracle.picture_copy(dp[0], bpc, 0.0)
+    got, lcs = oracle.f_ms_ssim(r0, d0)
+    want, wl = MN.ms_ssim(r0, d0)
+    assert lcs.shape == wl.shape == (5, 3)
+    np.testing.assert_allclose(lcs, wl, atol=2e-5)
+    assert abs(got - want) < 1e-5 and 0.5 < want < 1.0
