@@ -875,6 +875,9 @@ def main() -> int:
         out["workloads"] = workloads
     if sharded is not None:
         out["sharded_4k"] = sharded
+        out["e2e_sharded"] = {k: sharded.get(k) for k in ("value", "unit", "frames", "n_gpus", "scaling", "seconds",
+                                                          "pooled_vmaf_mean", "identical_to_n1", "resident_value")}
+        out["e2e_sharded"]["see"] = "sharded_4k (the full record)"
     if batch is not None:
         out["batch"] = batch
     extra = {}
