@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200vmaf.so")
+# B200VMAF_LIB: load another build of the library (kernel experiments); never set in normal use
+LIB_PATH = os.environ.get("B200VMAF_LIB") or os.path.join(_HERE, "libb200vmaf.so")
 
 BV_RAW_WORDS = 64
 BV_MAX_BATCH = 32
@@ -81,7 +82,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    if build_if_missing and not os.environ.get("B200VMAF_LIB"):
         from . import build as _build
         try:
             _build.build()
