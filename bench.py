@@ -100,6 +100,8 @@ def kernel_bytes(name: str, w: int, h: int, bps: int) -> float | None:
         if sc > 0:
             nw, nh = mw // 2 + (mw & 1), mh // 2 + (mh & 1)
             t[f"ms_ssim_lpf_s{sc}"] = (2 * mw * mh * (bps if sc == 1 else 4)) + 2 * nw * nh * 4
+            if sc == 1 and f in (2, 4, 8):
+                t["ms_ssim_lpf_s1"] += 2 * sp * 4          # it also writes float_ssim's decimated pair (fused staging)
             mw, mh = nw, nh
         t[f"ms_ssim_maps_s{sc}"] = 2 * mw * mh * (bps if sc == 0 else 4)
     return t.get(name)

@@ -11,12 +11,13 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORDER = {
-    # psnr=1 reads all three planes; the motion blur rides in f_vif_subsample_s1 (fused staging); its SAD follows that kernel
-    "1080p-float": ["psnr_sse_y", "psnr_sse_u", "psnr_sse_v", "f_vif_stat_s0", "f_vif_subsample_s1", "f_motion_sad",
+    # libvmaf psnr=1 is psnr_y; the motion blur rides in f_vif_subsample_s1 and float_ssim's box decimation in ms_ssim_lpf_s1
+    # (fused stagings); ssim_maps follows the MS-SSIM chain
+    "1080p-float": ["psnr_sse_y", "f_vif_stat_s0", "f_vif_subsample_s1", "f_motion_sad",
                     "f_vif_stat_s1", "f_vif_subsample_s2", "f_vif_stat_s2", "f_vif_subsample_s3", "f_vif_stat_s3", "f_adm_scale0",
-                    "f_adm_scale1", "f_adm_scale2", "f_adm_scale3", "ssim_decimate", "ssim_maps", "ms_ssim_maps_s0",
+                    "f_adm_scale1", "f_adm_scale2", "f_adm_scale3", "ms_ssim_maps_s0",
                     "ms_ssim_lpf_s1", "ms_ssim_maps_s1", "ms_ssim_lpf_s2", "ms_ssim_maps_s2", "ms_ssim_lpf_s3",
-                    "ms_ssim_maps_s3", "ms_ssim_lpf_s4", "ms_ssim_maps_s4", "f_reduce"],
+                    "ms_ssim_maps_s3", "ms_ssim_lpf_s4", "ms_ssim_maps_s4", "ssim_maps", "f_reduce"],
     # round 2: pyramid level 1 and the motion blur are produced by vif_stat_s0 (fused); the SAD follows the VIF chain
     "1080p-int": ["vif_stat_s0", "vif_stat_s1", "vif_subsample_s2", "vif_stat_s2", "vif_subsample_s3", "vif_stat_s3",
                   "motion_sad", "adm_scale0", "adm_scale1", "adm_scale2", "adm_scale3", "adm_rows_finish"],
