@@ -9,7 +9,7 @@ X="--steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras"
 # numbers printed under ncu are never bench values
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/r02_launches_$TAG.csv \
     python bench.py $X > $O/ncu_launches_$TAG.log 2>&1
-ncu --set full --clock-control none --launch-skip 1330 -c 29 -f -o $O/full_float_$TAG python bench.py $X > $O/ncu_full_float_$TAG.log 2>&1
+ncu --set full --clock-control none --launch-skip 1176 -c 26 -f -o $O/full_float_$TAG python bench.py $X > $O/ncu_full_float_$TAG.log 2>&1
 ncu -i $O/full_float_$TAG.ncu-rep --page raw --csv > $O/raw_float_$TAG.csv
 ncu --set full --clock-control none --launch-skip 590 -c 14 -f -o $O/full_int_$TAG python bench.py --workload 1080p-int $X > $O/ncu_full_int_$TAG.log 2>&1
 ncu -i $O/full_int_$TAG.ncu-rep --page raw --csv > $O/raw_int_$TAG.csv
