@@ -1,4 +1,4 @@
-"""Independent NumPy mirror of the integer VIF / integer motion / float VIF arithmetic -- TEST INFRASTRUCTURE.
+"""Independent NumPy mirror of the integer VIF / motion / ADM and float VIF / ADM / MS-SSIM arithmetic -- TEST INFRASTRUCTURE.
 
 A second restatement of libvmaf's published algorithm (integer_vif.c, integer_motion.c, vif.c / vif_tools.c; reached
 from the reference at app/vmaf_analyzer.py:417), written separately from
@@ -306,6 +306,143 @@ def adm_dwt_scale0(luma: np.ndarray, bpc: int = 8) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------------------
+# integer ADM, all four scales (integer_adm.c): DWT of the approximation band, decoupling through the Q30 reciprocal
+# table, fixed-point CSF, 3x3 contrast-masking threshold, per-row rounded cube sums -- whole-band int64 array code
+# ---------------------------------------------------------------------------------------------
+def _wrap(a: np.ndarray, bits: int) -> np.ndarray:
+    """what storing into intN_t does on two's-complement machines"""
+    half = 1 << (bits - 1)
+    return ((a + half) % (1 << bits)) - half
+
+
+def _adm_dwt_int(a_prev: np.ndarray, scale: int) -> np.ndarray:
+    """scales 1..3: the previous approximation band (int32 values) -> a, v, h, d.  Shifts after the vertical / horizontal
+    pass: scale 1: 0 / 15 (round 16384), scale 2: 16 / 16, scale 3: 16 / 15; 64-bit accumulation."""
+    sh_v, rnd_v = [(0, 0), (16, 32768), (16, 32768)][scale - 1]
+    sh_h, rnd_h = [(15, 16384), (16, 32768), (15, 16384)][scale - 1]
+    h, w = a_prev.shape
+    iy, jx = _dwt_index((h + 1) // 2, h), _dwt_index((w + 1) // 2, w)
+    rows = a_prev.astype(np.int64)[iy]                     # [oh, 4, w]
+    lo = _wrap((np.tensordot(rows, np.array(DWT_LO), axes=([1], [0])) + rnd_v) >> sh_v, 32)
+    hi = _wrap((np.tensordot(rows, np.array(DWT_HI), axes=([1], [0])) + rnd_v) >> sh_v, 32)
+    return np.stack([_wrap((src[:, jx] @ np.array(taps) + rnd_h) >> sh_h, 32)
+                     for src, taps in ((lo, DWT_LO), (lo, DWT_HI), (hi, DWT_LO), (hi, DWT_HI))])
+
+
+def _adm_recip(mag: np.ndarray) -> np.ndarray:
+    """div_lookup[32768 + m] for m in 0..32768: floor(2^30 / m), 0 at m == 0"""
+    return np.where(mag > 0, (1 << 30) // np.maximum(mag, 1), 0)
+
+
+def _adm_gain_k(o: np.ndarray, t: np.ndarray, scale: int) -> np.ndarray:
+    """k = clamp(t / o, 0, 1) in Q15.  Scale 0 (int16 bands): table entry of o itself; scales 1..3: |o| reduced to its 15
+    leading bits (rounded), the entry applied with o's sign and the extra shift."""
+    if scale == 0:
+        k = (np.sign(o) * _adm_recip(np.abs(o)) * t + 16384) >> 15
+    else:
+        ao = np.abs(o)
+        nbits = np.floor(np.log2(np.maximum(ao, 1).astype(np.float64))).astype(np.int64) + 1
+        sh = np.where(ao < 32768, 0, nbits - 15)
+        msb = np.where(ao < 32768, ao, (ao + (1 << np.maximum(sh - 1, 0))) >> sh)
+        k = (_adm_recip(msb) * t * np.sign(o) + (1 << (14 + sh))) >> (15 + sh)
+    return np.where(o == 0, 32768, np.clip(k, 0, 32768))
+
+
+def _rows_exact(a: np.ndarray) -> list:
+    """exact per-row sums of non-negative int64 values as Python integers (the C code keeps them in 64 bits)"""
+    lo, hi = a & 0xFFFFFFFF, a >> 32
+    return [int(l) + (int(h_) << 32) for l, h_ in zip(lo.sum(axis=1), hi.sum(axis=1))]
+
+
+def adm_int(ref: np.ndarray, dis: np.ndarray, bpc: int = 8, egl: float = 100.0, view_dist: float = 3.0,
+            display_h: int = 1080):
+    """-> (cm int [4][3], den int [4][3]): the contrast-masked numerator and the CSF denominator accumulators of integer ADM
+    per scale for the bands (h, v, d) -- layout of oracle.adm()['cm'] / ['den']."""
+    f32, f64, i64 = np.float32, np.float64, np.int64
+    cos2 = f32(np.cos(np.pi / 180.0) * np.cos(np.pi / 180.0))
+    rb, db = adm_dwt_scale0(ref, bpc), adm_dwt_scale0(dis, bpc)
+    cms, dens = [], []
+    for scale in range(4):
+        if scale:
+            rb, db = _adm_dwt_int(rb[0], scale), _adm_dwt_int(db[0], scale)
+        h, w = rb[0].shape
+        O, T = [rb[2], rb[1], rb[3]], [db[2], db[1], db[3]]          # (h, v, d); stack order is a, v, h, d
+        rf = rfactor(scale, view_dist, display_h)
+        if scale == 0:
+            i_rf = [36453, 36453, 49417] if abs(view_dist * display_h - 3240.0) < 1e-8 else \
+                   [int(float(rf[0]) * 2 ** 21) & 0xFFFF, int(float(rf[1]) * 2 ** 21) & 0xFFFF, int(float(rf[2]) * 2 ** 23) & 0xFFFF]
+        else:
+            i_rf = [int(float(r) * 2.0 ** 32) for r in rf]
+        # angle test: inner product and squared magnitudes of the (h, v) vectors, through float then double as the C does
+        q = lambda v: v.astype(f32).astype(f64) / 4096.0
+        ot, om, tm = q(O[0] * T[0] + O[1] * T[1]), q(O[0] * O[0] + O[1] * O[1]), q(T[0] * T[0] + T[1] * T[1])
+        flag = (ot >= 0) & (ot * ot >= f64(cos2) * om * tm)
+        R, CA, CF = [], [], []
+        for b in range(3):
+            o, t = O[b], T[b]
+            k = _adm_gain_k(o, t, scale)
+            rst = (k * o + 16384) >> 15
+            if scale == 0:
+                rst = _wrap(rst, 16)
+            sgn = (k.astype(f32) / f32(32768)) * (o.astype(f32) / f32(64))
+            v, tt = rst.astype(f64) * egl, t.astype(f64)
+            lim = np.where(sgn > 0, np.minimum(v, tt), np.maximum(v, tt))
+            rst = np.where(flag & (sgn != 0), np.trunc(lim).astype(i64), rst)
+            a = t - rst
+            if scale == 0:
+                rst, a = _wrap(rst, 16), _wrap(a, 16)
+                ca = _wrap((_wrap(i_rf[b] * a, 32) + [16384, 16384, 65536][b]) >> [15, 15, 17][b], 16)
+                cf = _wrap((4369 * np.abs(ca) + 2048) >> 12, 16)
+            else:
+                ca = _wrap((i_rf[b] * a + (1 << 27)) >> 28, 32)
+                cf = _wrap((143165577 * np.abs(ca) + (1 << 31)) >> 32, 32)
+            R.append(rst); CA.append(ca); CF.append(cf)
+        left, top = int(w * 0.1 - 0.5), int(h * 0.1 - 0.5)
+        right, bottom = w - left, h - top
+        ys, xs = slice(top, bottom), slice(left, right)
+        # threshold: over the three bands, the eight neighbours' |csf| / 30 plus the centre's |csf| / 15
+        thr = np.zeros((bottom - top, right - left), i64)
+        for b in range(3):
+            cfp = _pad_mirror(_pad_mirror(CF[b], 1, 0), 1, 1)
+            box = sum(cfp[top + 1 + di:bottom + 1 + di, left + 1 + dj:right + 1 + dj] for di in (-1, 0, 1) for dj in (-1, 0, 1))
+            c = np.abs(CA[b][ys, xs])
+            centre = _wrap((8738 * c + 2048) >> 12, 16) if scale == 0 else _wrap((286331153 * c + (1 << 31)) >> 32, 32)
+            thr = _wrap(thr + _wrap(box - CF[b][ys, xs] + centre, 32), 32)
+        lg = lambda n: int(np.ceil(np.log2(n)))
+        if scale == 0:
+            sh_sub, sh_sq = [10, 10, 12], [29, 29, 30]
+            sh_cub = [int(np.ceil(np.log2(w) - 4)), int(np.ceil(np.log2(w) - 4)), int(np.ceil(np.log2(w) - 3))]
+        else:
+            sh_sub, sh_sq, sh_cub = [0, 0, 0], [30, 30, 30], [lg(w)] * 3
+        sh_in = lg(h)
+        cm = []
+        for b in range(3):
+            x = _wrap(R[b][ys, xs] * i_rf[b], 32) if scale == 0 else _wrap((R[b][ys, xs] * i_rf[b] + (1 << 27)) >> 28, 32)
+            x = np.maximum(_wrap(np.abs(x) - _wrap(thr << sh_sub[b], 32), 32), 0)
+            x_sq = _wrap((x * x + (1 << (sh_sq[b] - 1))) >> sh_sq[b], 32)
+            val = (x_sq * x + int(2.0 ** (sh_cub[b] - 1))) >> sh_cub[b]
+            cm.append(sum((r + int(2.0 ** (sh_in - 1))) >> sh_in for r in _rows_exact(val)))
+        cms.append(cm)
+        # denominator: cubes of the reference bands over the same region, rounded per row
+        dn = []
+        for b in range(3):
+            v = np.abs(O[b][ys, xs])
+            if scale == 0:
+                v = v & 0xFFFF
+                sh_acc = max(int(np.ceil(np.log2((bottom - top) * (right - left)) - 20)), 0)
+                add_acc = (1 << (sh_acc - 1)) if sh_acc > 0 else 0
+                rows = _rows_exact(v * v * v)
+            else:
+                sh_sqd = [31, 30, 31][scale - 1]
+                sh_c, sh_acc = lg(right - left), lg(bottom - top)
+                add_acc = int(2.0 ** (sh_acc - 1))
+                rows = _rows_exact(((((v * v + (1 << (sh_sqd - 1))) >> sh_sqd) * v) + int(2.0 ** (sh_c - 1))) >> sh_c)
+            dn.append(sum((r + add_acc) >> sh_acc for r in rows))
+        dens.append(dn)
+    return cms, dens
+
+
+# ---------------------------------------------------------------------------------------------
 # float ADM (adm.c / adm_tools.c): DWT, decoupling, CSF, contrast masking -- whole-plane fp32 array code
 # ---------------------------------------------------------------------------------------------
 DWT_LO_F = np.array([0.482962913144690, 0.836516303737469, 0.224143868041857, -0.129409522550921], np.float32)
@@ -323,7 +460,8 @@ def rfactor(scale: int, view_dist: float = 3.0, display_h: int = 1080) -> np.nda
     for theta in (1, 1, 2):
         r = f32(view_dist * display_h * np.pi / 180.0)
         temp = f32(np.log10(2.0 ** (scale + 1) * float(f32(0.401)) * float(f32(g[theta])) / float(r)))
-        q = f32(2.0 * float(f32(0.495)) * 10.0 ** (float(f32(0.466)) * float(temp) * float(temp)) / float(f32(amp[scale][theta])))
+        ktt = f32(f32(f32(0.466) * temp) * temp)             # float * float * float: evaluated in float
+        q = f32(2.0 * float(f32(0.495)) * 10.0 ** float(ktt) / float(f32(amp[scale][theta])))
         out.append(f32(1.0) / q)
     return np.array(out, np.float32)
 

@@ -95,6 +95,31 @@ def test_integer_adm_scale0_wavelet_bands_agree(seed, w, h, bpc):
     assert np.abs(want[1:]).max() > 0                     # the detail bands are not trivially zero
 
 
+@pytest.mark.parametrize("seed,w,h,bpc,egl,vd,dh", [
+    (3, 176, 144, 8, 100.0, 3.0, 1080), (5, 161, 97, 8, 1.0, 3.0, 1080), (8, 208, 120, 10, 100.0, 3.0, 1080),
+    (9, 242, 137, 12, 1.2, 3.0, 1080), (4, 352, 288, 8, 100.0, 2.5, 720), (2, 64, 48, 8, 100.0, 3.0, 1080)])
+def test_integer_adm_accumulators_agree(seed, w, h, bpc, egl, vd, dh):
+    """Integer ADM end to end -- four wavelet levels with their per-scale shifts, the Q30 reciprocal table with the
+    15-bit reduction of large divisors, the 1-degree angle test, the enhancement-gain limit, fixed-point CSF (hard-coded
+    integers at the default viewing condition, derived ones otherwise), the 3x3 threshold with folded band edges, per-row
+    rounding of both cube sums -- as whole-band array code against the C oracle's per-pixel loops: all 24 raw accumulators
+    of a frame, bit for bit."""
+    rp, dp = synth.frame_pair(seed, 1, w, h, bpc, chroma=False)
+    c = oracle.adm(rp[0], dp[0], bpc, egl, vd, dh)
+    cm, dn = MN.adm_int(rp[0], dp[0], bpc, egl, vd, dh)
+    assert [[int(v) for v in r] for r in c["cm"]] == cm
+    assert [[int(v) for v in r] for r in c["den"]] == dn
+    assert all(v > 0 for r in cm for v in r) and all(v > 0 for r in dn for v in r)
+
+
+def test_integer_adm_gain_limit_moves_the_numerator_only():
+    """The limit acts where the angle test passes: a tight limit changes the numerator accumulators and leaves the
+    denominator (reference only) alone, in the mirror as in the oracle."""
+    rp, dp = synth.frame_pair(5, 1, 161, 97, 8, chroma=False)
+    loose, tight = MN.adm_int(rp[0], dp[0], 8, 100.0), MN.adm_int(rp[0], dp[0], 8, 1.0)
+    assert loose[1] == tight[1] and loose[0] != tight[0]
+
+
 @pytest.mark.parametrize("seed,w,h,bpc,egl", [(3, 176, 144, 8, 100.0), (5, 322, 242, 8, 1.0), (8, 208, 120, 10, 100.0)])
 def test_float_adm_agrees(seed, w, h, bpc, egl):
     """float ADM (DWT, decoupling with the 1-degree angle test and the gain limit, CSF, 3x3 contrast-masking threshold, cube
@@ -113,7 +138,7 @@ def test_csf_factors_follow_the_watson_model():
     listed = [(0.0173815, 0.0058907), (0.0319848, 0.0142991), (0.0433727, 0.0243969), (0.0456734, 0.0313127)]
     for s in range(4):
         a, b = MN.rfactor(s), oracle.adm_rfactor(s)
-        np.testing.assert_allclose(a, b, rtol=3e-7)
+        np.testing.assert_array_equal(a, b)               # `k * temp * temp` is float arithmetic in adm_tools.h
         assert abs(a[0] - listed[s][0]) < 5e-7 and a[0] == a[1] and abs(a[2] - listed[s][1]) < 5e-7
     # the integer path's hard-coded scale-0 factors (include/libvmaf_spec.h, tagged L) against the model
     assert abs(36453 / 2.0 ** 21 - MN.rfactor(0)[0]) < 1e-6 and abs(49417 / 2.0 ** 23 - MN.rfactor(0)[2]) < 1e-6
