@@ -599,3 +599,70 @@ def ms_ssim(ref0: np.ndarray, dis0: np.ndarray):
                   np.mean((cv + c3) / (sr + c3))]
         score *= (lcs[s, 0] ** (expo[4] if s == 4 else 0.0)) * lcs[s, 1] ** expo[s] * lcs[s, 2] ** expo[s]
     return score, lcs
+
+
+# ---------------------------------------------------------------------------------------------
+# FFmpeg `ssim` filter (libavfilter/vf_ssim.c): 4x4 block sums, overlapping 8x8 windows, float row sums
+# ---------------------------------------------------------------------------------------------
+def ffssim_plane(a: np.ndarray, b: np.ndarray, bpc: int = 8) -> float:
+    f32 = np.float32
+    h, w = a.shape
+    h4, w4 = h >> 2, w >> 2
+    if h4 < 2 or w4 < 2:
+        return 1.0
+    p = a[:h4 * 4, :w4 * 4].astype(np.int64).reshape(h4, 4, w4, 4)
+    q = b[:h4 * 4, :w4 * 4].astype(np.int64).reshape(h4, 4, w4, 4)
+    win = lambda s: s[:-1, :-1] + s[:-1, 1:] + s[1:, :-1] + s[1:, 1:]          # four 4x4 blocks = one 8x8 window
+    s1, s2 = win(p.sum(axis=(1, 3))), win(q.sum(axis=(1, 3)))
+    ss, s12 = win((p * p + q * q).sum(axis=(1, 3))), win((p * q).sum(axis=(1, 3)))
+    peak = (1 << bpc) - 1
+    c1, c2 = int(.01 * .01 * peak * peak * 64 + .5), int(.03 * .03 * peak * peak * 64 * 63 + .5)
+    var, cov = ss * 64 - s1 * s1 - s2 * s2, s12 * 64 - s1 * s2
+    v = ((2 * s1 * s2 + c1).astype(f32) * (2 * cov + c2).astype(f32)) / \
+        ((s1 * s1 + s2 * s2 + c1).astype(f32) * (var + c2).astype(f32))
+    rows = np.cumsum(v, axis=1, dtype=f32)[:, -1]                              # vf_ssim sums a row of windows in float
+    return float(rows.astype(np.float64).sum() / ((h4 - 1) * (w4 - 1)))
+
+
+def sse_plane(a: np.ndarray, b: np.ndarray) -> int:
+    d = a.astype(np.int64) - b.astype(np.int64)
+    return int((d * d).sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# float motion (motion.c): 5-tap blur, mean absolute difference of consecutive blurred frames
+# ---------------------------------------------------------------------------------------------
+MOTION_TAPS_F = np.array([0.054488685, 0.244201342, 0.402619947, 0.244201342, 0.054488685], np.float32)
+
+
+def motion_blur_float(luma_f: np.ndarray, taps=MOTION_TAPS_F) -> np.ndarray:
+    return _fir_f32(_fir_f32(luma_f.astype(np.float32), taps, 0), taps, 1)
+
+
+def motion_sad_float(a: np.ndarray, b: np.ndarray) -> float:
+    """a float sum per row, the rows added into another float, divided by the sample count in float"""
+    f32 = np.float32
+    rows = np.cumsum(np.abs((a - b).astype(f32)), axis=1, dtype=f32)[:, -1]
+    return float(f32(np.cumsum(rows, dtype=f32)[-1] / f32(a.shape[0] * a.shape[1])))
+
+
+# ---------------------------------------------------------------------------------------------
+# iqa SSIM (ssim.c) at one scale, after the f x f box decimation float_ssim applies to large pictures -- float64
+# ---------------------------------------------------------------------------------------------
+def _decimate_box(a: np.ndarray, f: int) -> np.ndarray:
+    h, w = a.shape
+    dh, dw = h // f + (h & 1), w // f + (w & 1)
+    iy, jx = _sym_index(dh, h, f, -(f // 2), f), _sym_index(dw, w, f, -(f // 2), f)
+    return a[iy][:, :, jx].sum(axis=(1, 3)) / (f * f)
+
+
+def ssim_float(ref0: np.ndarray, dis0: np.ndarray) -> float:
+    """luma as float in [0, 255]; decimation factor max(1, round(min(w, h) / 256))"""
+    r, c = ref0.astype(np.float64), dis0.astype(np.float64)
+    f = max(1, int(np.floor(min(r.shape) / 256.0 + 0.5)))
+    if f > 1:
+        r, c = _decimate_box(r, f), _decimate_box(c, f)
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    m1, m2 = _valid11(r), _valid11(c)
+    v1, v2, cv = _valid11(r * r) - m1 * m1, _valid11(c * c) - m2 * m2, _valid11(r * c) - m1 * m2
+    return float(np.mean((2 * m1 * m2 + c1) * (2 * cv + c2) / ((m1 * m1 + m2 * m2 + c1) * (v1 + v2 + c2))))

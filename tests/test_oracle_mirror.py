@@ -156,3 +156,37 @@ def test_ms_ssim_agrees_with_a_float64_restatement(seed, w, h, bpc):
     assert lcs.shape == wl.shape == (5, 3)
     np.testing.assert_allclose(lcs, wl, atol=2e-5)
     assert abs(got - want) < 1e-5 and 0.5 < want < 1.0
+
+
+@pytest.mark.parametrize("seed,w,h,bpc", [(3, 176, 144, 8), (5, 161, 97, 8), (8, 208, 120, 10), (9, 242, 137, 12)])
+def test_ffmpeg_ssim_and_sse_agree(seed, w, h, bpc):
+    """FFmpeg's ssim filter (integer 4x4 block sums, 8x8 windows, float window score, float row sums) and the squared error
+    both psnr flavours start from, on every plane of a 4:2:0 pair; 8-bit constants 416 / 235963 fall out of the formula."""
+    rp, dp = synth.frame_pair(seed, 1, w, h, bpc)
+    for k in range(3):
+        assert oracle.ffssim_plane(rp[k], dp[k], bpc) == MN.ffssim_plane(rp[k], dp[k], bpc)
+        assert int(oracle.sse(rp[k], dp[k], bpc)) == MN.sse_plane(rp[k], dp[k])
+    assert 0.2 < MN.ffssim_plane(rp[0], dp[0], bpc) < 1.0
+    assert (int(.01 * .01 * 255 * 255 * 64 + .5), int(.03 * .03 * 255 * 255 * 64 * 63 + .5)) == (416, 235963)
+
+
+@pytest.mark.parametrize("seed,w,h,bpc", [(3, 176, 144, 8), (5, 161, 97, 8), (8, 208, 120, 10)])
+def test_float_motion_agrees(seed, w, h, bpc):
+    """float motion: blurred planes value for value (fp32, taps left to right), SAD with a float sum per row."""
+    a, _ = synth.frame_pair(seed, 0, w, h, bpc, chroma=False)
+    b, _ = synth.frame_pair(seed, 1, w, h, bpc, chroma=False)
+    fa, fb = oracle.picture_copy(a[0], bpc, -128.0), oracle.picture_copy(b[0], bpc, -128.0)
+    ba, bb = oracle.f_motion_blur(fa), oracle.f_motion_blur(fb)
+    ma, mb = MN.motion_blur_float(fa), MN.motion_blur_float(fb)
+    np.testing.assert_array_equal(ba, ma)
+    np.testing.assert_array_equal(bb, mb)
+    assert oracle.f_motion_sad(ba, bb) == MN.motion_sad_float(ma, mb) > 0.5
+
+
+@pytest.mark.parametrize("seed,w,h,bpc", [(3, 176, 144, 8), (8, 208, 120, 10), (4, 640, 540, 8), (6, 1000, 780, 8)])
+def test_float_ssim_agrees_with_a_float64_restatement(seed, w, h, bpc):
+    """float_ssim incl. the box decimation of large pictures (factor 2 at 640x540, 3 at 1000x780, odd factor = centred
+    window): the fp32 oracle against float64 array code; the fp32 variance subtraction is worth ~2e-6."""
+    rp, dp = synth.frame_pair(seed, 1, w, h, bpc, chroma=False)
+    r0, c0 = oracle.picture_copy(rp[0], bpc, 0.0), oracle.picture_copy(dp[0], bpc, 0.0)
+    assert abs(oracle.f_ssim(r0, c0) - MN.ssim_float(r0, c0)) < 5e-6
