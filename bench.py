@@ -237,7 +237,7 @@ def cpu_baseline(wl: dict, frames_per_core: int = 0) -> dict:
     n = cores * frames_per_core
     return {"value": n / max(busy), "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": f"{n} synthetic {wl['w']}x{wl['h']} {wl['bpc']}-bit frame pairs ({frames_per_core} per core), "
-                      f"oracle/ ({'float' if kind == 'float' else 'integer'} extractors, scalar C -O2); "
+                      f"oracle/ ({'float' if kind == 'float' else 'integer'} extractors, scalar C -O3); "
                       f"wall {dt:.1f}s incl. frame synthesis"}
 
 

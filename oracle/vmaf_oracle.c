@@ -19,7 +19,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
  * may call into this file.  The product path (pqa2_b200/) never does.
  *
- * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off: no FMA contraction, so the few
+ * Build: see oracle/Makefile (gcc -O3 -ffp-contract=off: no FMA contraction, so the few
  * float/double steps evaluate exactly as written).
  */
 #include "../include/libvmaf_spec.h"
