@@ -16,7 +16,8 @@ sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 from pqa2_b200 import synth  # noqa: E402
 
-CASES = [dict(seed=3, w=176, h=144, bpc=8, n=3), dict(seed=8, w=208, h=120, bpc=10, n=2)]
+CASES = [dict(seed=3, w=176, h=144, bpc=8, n=3), dict(seed=8, w=208, h=120, bpc=10, n=2),
+         dict(seed=5, w=161, h=97, bpc=8, n=2), dict(seed=9, w=242, h=178, bpc=12, n=2)]
 
 
 def main():
