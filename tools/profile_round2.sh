@@ -11,16 +11,18 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
     python bench.py $X > $O/ncu_launches_$TAG.log 2>&1
 ncu --set full --clock-control none --launch-skip 1176 -c 26 -f -o $O/full_float_$TAG python bench.py $X > $O/ncu_full_float_$TAG.log 2>&1
 ncu -i $O/full_float_$TAG.ncu-rep --page raw --csv > $O/raw_float_$TAG.csv
+if [ -z "$FLOAT_ONLY" ]; then      # FLOAT_ONLY=1: only bv_float.cu changed since the last full run
 ncu --set full --clock-control none --launch-skip 590 -c 14 -f -o $O/full_int_$TAG python bench.py --workload 1080p-int $X > $O/ncu_full_int_$TAG.log 2>&1
 ncu -i $O/full_int_$TAG.ncu-rep --page raw --csv > $O/raw_int_$TAG.csv
 ncu --set full --clock-control none --launch-skip 590 -c 14 -f -o $O/full_4k_$TAG python bench.py --workload 4k-int $X > $O/ncu_full_4k_$TAG.log 2>&1
 ncu -i $O/full_4k_$TAG.ncu-rep --page raw --csv > $O/raw_4k_$TAG.csv
+fi
 rm -f $O/full_float_$TAG.ncu-rep $O/full_int_$TAG.ncu-rep $O/full_4k_$TAG.ncu-rep
 ls -la $O | tail -12
 # source-level capture of the two dominant kernels (dynamic SASS opcode histogram, per-line counters)
-tools/prof_src.sh 1080p-int "^vif_stat_kernel" 1 r02_int_vif0 || true
+[ -z "$FLOAT_ONLY" ] && { tools/prof_src.sh 1080p-int "^vif_stat_kernel" 1 r02_int_vif0 || true; }
 tools/prof_src.sh 1080p-float "^f_vif_stat_kernel" 1 r02_f_vif0 || true
-python tools/sass_hist.py $O/src_r02_int_vif0.csv 66355200 > $O/r02_sass_dyn_vif_stat_s0.txt 2>&1 || true
+[ -z "$FLOAT_ONLY" ] && { python tools/sass_hist.py $O/src_r02_int_vif0.csv 66355200 > $O/r02_sass_dyn_vif_stat_s0.txt 2>&1 || true; }
 python tools/sass_hist.py $O/src_r02_f_vif0.csv 66355200 > $O/r02_sass_dyn_f_vif_stat_s0.txt 2>&1 || true
 rm -f $O/src_r02_int_vif0.csv $O/src_r02_f_vif0.csv
 ls -la $O | tail -8
