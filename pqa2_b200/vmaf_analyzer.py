@@ -11,7 +11,8 @@ stats-file layout; reference
 Differences, all forced by the environment:
 * PyQt5 is optional.  Without it the four signals are plain objects with ``connect`` / ``emit``.
 * Inputs are raw planar video (``.y4m`` or headerless ``.yuv`` with a ``_WxH`` name hint) or, when cv2 is
-  installed, containers (``.mp4`` ...) decoded by its bundled libavcodec -- luma only, which is all VMAF reads.
+  installed, containers (``.mp4`` ...) decoded by its bundled libavformat / libavcodec (``avdec``: Y, U, V as ffmpeg
+  would deliver them; through ``cv2.VideoCapture`` -- luma only -- if those libraries cannot be driven directly).
 * ``threads`` (libvmaf ``n_threads``) is accepted and ignored: the work runs on the GPUs in
   ``devices`` (default: every visible B200), frame-sharded with a one-frame lead-in per shard.
 """
@@ -223,7 +224,7 @@ class VMAFAnalyzer(QObject):
                                    # `motion` extractor (the vif_scaleN / adm2 items name no extractor of their own
                                    # and the last `feature=` wins), so both flags add `motion` / `motion2` to the log
                                    float_motion=bool(self.enable_motion_score or self.enable_temporal_features))
-        if ref_info.decoder == "cv2" or dis_info.decoder == "cv2":
+        if ref_info.decoder != "raw" or dis_info.decoder != "raw":
             # container decode is sequential (seeking is not frame-exact): one shard, one decoder per file
             devices = tuple(devices)[:1]
         src = engine.FileSource(ref_info, dis_info)

@@ -2,8 +2,8 @@
 
 The reference hands ffmpeg two container files (``app/vmaf_analyzer.py:415-416``) and lets it
 decode; libvmaf then sees planar pictures, 8-bit as u8 and >8-bit as little-endian u16
-(SURVEY.md Appendix A.1).  This engine consumes those planar pictures directly.  Compressed
-inputs (the reference's aligned MP4s) are out of scope for this round."""
+(SURVEY.md Appendix A.1).  This engine consumes those planar pictures directly; compressed inputs (the
+reference's aligned MP4s) are decoded on the host by the libavcodec inside the cv2 wheel (``avdec``)."""
 from __future__ import annotations
 
 import os
@@ -25,7 +25,8 @@ class ClipInfo:
     nb_frames: int = 0
     header_bytes: int = 0
     frame_header_bytes: int = 0
-    decoder: str = "raw"          # "raw" (y4m / planar yuv) or "cv2" (container decoded by cv2's bundled libavcodec, luma only)
+    decoder: str = "raw"          # "raw" (y4m / planar yuv), "av" (container through the cv2 wheel's libavcodec: all planes)
+                                  # or "cv2" (container through cv2.VideoCapture: luma only)
     codec_name: str = "rawvideo"  # ffprobe's codec_name (app/vmaf_analyzer.py:221-231); containers report their stream's codec
 
     @property
@@ -123,10 +124,12 @@ _CONTAINER_EXT = {".mp4", ".mov", ".mkv", ".avi", ".m4v", ".webm", ".ts"}
 
 
 def _probe_container(path: str) -> ClipInfo:
-    """Compressed clips (the reference's aligned H.264 MP4s, app/bookend_alignment.py:526-536) through the
-    libavcodec that ships inside cv2.  With CAP_PROP_CONVERT_RGB off cv2 hands back the decoder's luma plane
-    untouched, which is all the VMAF extractors, psnr_y, float_ssim and float_ms_ssim read; chroma is not
-    exposed, so such clips are described as 8-bit luma-only (chroma-plane stats files are skipped for them)."""
+    """Compressed clips (the reference's aligned H.264 MP4s, app/bookend_alignment.py:526-536).  Preferred decoder:
+    ``avdec`` -- the libavformat / libavcodec that ship inside the cv2 wheel, driven directly, which yields Y, U and V as
+    the reference's ffmpeg child would hand them to libvmaf and to the psnr / ssim filters.  Without it: cv2's
+    VideoCapture, which with CAP_PROP_CONVERT_RGB off hands back the decoder's luma plane untouched and nothing else, so
+    such clips are described as 8-bit luma-only (enough for VMAF, psnr_y, float_ssim, float_ms_ssim; the all-plane
+    stats files are skipped)."""
     try:
         import cv2
     except Exception as e:                                  # noqa: BLE001
@@ -136,7 +139,7 @@ def _probe_container(path: str) -> ClipInfo:
         if not cap.isOpened():
             raise ValueError(f"{path}: cv2 cannot open this file")
         w, h = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
-        n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))          # the container's own count, or duration x rate: an estimate
         fps = float(cap.get(cv2.CAP_PROP_FPS)) or 30.0
         cc = int(cap.get(cv2.CAP_PROP_FOURCC))
     finally:
@@ -144,6 +147,14 @@ def _probe_container(path: str) -> ClipInfo:
     if w <= 0 or h <= 0:
         raise ValueError(f"{path}: no video stream")
     tag = "".join(chr((cc >> (8 * k)) & 0xFF) for k in range(4)).strip("\0 ").lower()
+    from . import avdec
+    if avdec.available():
+        try:
+            with avdec.AvDecoder(path, threads=1) as d:
+                return ClipInfo(path, d.width, d.height, d.bpc, d.chroma, d.fps_num, d.fps_den, nb_frames=n, decoder="av",
+                                codec_name=d.codec_name)
+        except (RuntimeError, ValueError):                  # layout check failed / unsupported pixel format: luma via cv2
+            pass
     return ClipInfo(path, w, h, 8, 400, int(round(fps * 1000)), 1000, nb_frames=n, decoder="cv2",
                     codec_name=_FOURCC_CODEC.get(tag, tag or "unknown"))
 
@@ -212,12 +223,60 @@ class _Cv2Reader:
         planes[0][...] = y
 
 
+class _AvReader:
+    """All planes of a container file through avdec (libavformat / libavcodec).  Strictly sequential, like _Cv2Reader:
+    a frame further ahead is reached by decoding and discarding, a frame behind the cursor by reopening the file."""
+
+    def __init__(self, info: ClipInfo):
+        self.info = info
+        self._dec = None
+        self._dtype = np.uint8 if info.bpc == 8 else np.dtype("<u2")
+        self._open()
+
+    def _open(self):
+        from . import avdec
+        if self._dec is not None:
+            self._dec.close()
+        self._dec = avdec.AvDecoder(self.info.path)
+        d, inf = self._dec, self.info
+        if (d.width, d.height, d.bpc, d.chroma) != (inf.width, inf.height, inf.bpc, inf.chroma):
+            raise ValueError(f"{inf.path}: stream changed since it was probed")
+        self._next = 0
+
+    def close(self):
+        if self._dec is not None:
+            self._dec.close()
+            self._dec = None
+
+    def alloc_planes(self, pinned: bool = True):
+        if pinned:
+            from .extractor import pinned_empty
+            return [pinned_empty(s, self._dtype) for s in self.info.plane_shapes()]
+        return [np.empty(s, self._dtype) for s in self.info.plane_shapes()]
+
+    def read_into(self, i: int, planes, luma_only: bool = False) -> None:
+        if i < self._next:
+            self._open()
+        while self._next < i:
+            if not self._dec.next():
+                raise EndOfClip(f"{self.info.path}: stream ends at frame {self._next}")
+            self._next += 1
+        if not self._dec.next(planes, luma_only):
+            if i == 0:
+                raise EOFError(f"{self.info.path}: cannot decode the first frame")
+            raise EndOfClip(f"{self.info.path}: stream ends at frame {i}")
+        self._next = i + 1
+
+
 class ClipReader:
     """Sequential / random access reader that fills caller-provided (pinned) plane arrays."""
 
     def __new__(cls, info: ClipInfo):
-        if getattr(info, "decoder", "raw") == "cv2":
+        dec = getattr(info, "decoder", "raw")
+        if dec == "cv2":
             return _Cv2Reader(info)
+        if dec == "av":
+            return _AvReader(info)
         return super().__new__(cls)
 
     def __init__(self, info: ClipInfo):

@@ -176,29 +176,43 @@ def test_two_rank_gloo_matches_single_process(n):
     assert D.rank_range(7, 0, 2) == (0, 3) and D.rank_range(7, 1, 2) == (3, 7) and D.rank_range(1, 1, 2) == (1, 1)
 
 
-def test_container_decode_through_cv2(tmp_path):
-    """Row f2 (decode): compressed clips come in through cv2's bundled libavcodec, luma plane untouched."""
+def _write_mp4(cv2, path, frames_bgr, w, h, fourcc="mp4v"):
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*fourcc), 25, (w, h))
+    if not wr.isOpened():
+        pytest.skip(f"cv2 cannot encode {fourcc} here")
+    for fr in frames_bgr:
+        wr.write(fr)
+    wr.release()
+
+
+@pytest.mark.parametrize("decoder", ["av", "cv2"])
+def test_container_decode(tmp_path, monkeypatch, decoder):
+    """Row f2 (decode): compressed clips come in through the libavformat / libavcodec inside the cv2 wheel -- all three
+    planes (`av`), or through cv2.VideoCapture when those libraries cannot be driven -- luma only (`cv2`)."""
     cv2 = pytest.importorskip("cv2")
-    from pqa2_b200 import synth
+    from pqa2_b200 import avdec, synth
+    if decoder == "av" and not avdec.available():
+        pytest.skip("the cv2 wheel's FFmpeg libraries are not usable here")
+    if decoder == "cv2":
+        monkeypatch.setattr(avdec, "available", lambda: False)
     w, h, n = 320, 176, 6
     path = str(tmp_path / "clip.mp4")
-    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 25, (w, h))
-    if not wr.isOpened():
-        pytest.skip("cv2 cannot encode mp4v here")
     lum = [synth.ref_luma(1, f, w, h) for f in range(n)]
-    for y in lum:
-        wr.write(cv2.cvtColor(y, cv2.COLOR_GRAY2BGR))
-    wr.release()
+    _write_mp4(cv2, path, [cv2.cvtColor(y, cv2.COLOR_GRAY2BGR) for y in lum], w, h)
     info = yuvio.probe(path)
-    assert (info.width, info.height, info.bpc, info.chroma, info.nb_frames, info.decoder) == (w, h, 8, 400, n, "cv2")
+    chroma = 420 if decoder == "av" else 400
+    assert (info.width, info.height, info.bpc, info.chroma, info.nb_frames, info.decoder) == (w, h, 8, chroma, n, decoder)
     assert abs(info.fps - 25.0) < 1e-6
     r = yuvio.ClipReader(info)
     pl = r.alloc_planes(pinned=False)
+    assert len(pl) == (3 if decoder == "av" else 1)
     for f in (0, 1, 4, 2):                       # sequential and seeking reads
-        r.read_into(f, pl, True)
+        r.read_into(f, pl, decoder == "cv2")
         # limited-range luma of a lossy encode: 16 + 219/255 * gray, within a few code values on average
         want = 16.0 + lum[f].astype(np.float64) * (219.0 / 255.0)
         assert pl[0].shape == (h, w) and np.abs(pl[0] - want).mean() < 4.0
+        if decoder == "av":                      # a grey picture: both chroma planes sit at 128
+            assert pl[1].shape == (h // 2, w // 2) and abs(pl[1].mean() - 128) < 2 and abs(pl[2].mean() - 128) < 2
     # past the decodable end: the clip ends there (ffmpeg + libvmaf stop at the shorter input), no seek involved
     with pytest.raises(yuvio.EndOfClip):
         r.read_into(n + 3, pl, True)
@@ -208,6 +222,56 @@ def test_container_decode_through_cv2(tmp_path):
     meta = VMAFAnalyzer().get_video_metadata(path)
     assert meta["width"] == w and meta["nb_frames"] == n
     assert meta["codec_name"] == "mpeg4"         # ffprobe's name of the stream's codec, not "rawvideo"
+
+
+@pytest.mark.parametrize("fourcc,ext", [("mp4v", "mp4"), ("MJPG", "avi")])
+def test_avdec_planes_are_the_decoders(tmp_path, fourcc, ext):
+    """avdec against cv2's own use of the same libavcodec: the luma plane is identical to what VideoCapture hands back
+    raw, and Y, U, V converted to BGR reproduce VideoCapture's BGR output to within the two conversions' rounding (a
+    swapped or misaligned chroma plane would be off by tens of code values on this colourful clip).  MJPG decodes to a
+    full-range `yuvj` format: same planes."""
+    cv2 = pytest.importorskip("cv2")
+    from pqa2_b200 import avdec
+    if not avdec.available():
+        pytest.skip("the cv2 wheel's FFmpeg libraries are not usable here")
+    w, h, n = 208, 112, 5
+    yy, xx = np.mgrid[0:h, 0:w]
+    frames = []
+    for f in range(n):
+        b = (96 + 90 * np.sin(xx / 17.0 + f)).astype(np.uint8)
+        g = (128 + 100 * np.cos(yy / 13.0 - f)).astype(np.uint8)
+        r_ = ((xx * 255) // w).astype(np.uint8)
+        frames.append(cv2.GaussianBlur(np.dstack([b, g, r_]), (5, 5), 1.5))
+    path = str(tmp_path / f"clip.{ext}")
+    _write_mp4(cv2, path, frames, w, h, fourcc)
+    raw, bgr = cv2.VideoCapture(path), cv2.VideoCapture(path)
+    raw.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    with avdec.AvDecoder(path) as d:
+        assert (d.width, d.height, d.bpc) == (w, h, 8) and d.chroma in (420, 422, 444)
+        assert d.codec_name == {"mp4v": "mpeg4", "MJPG": "mjpeg"}[fourcc] and (d.fps_num, d.fps_den) == (25, 1)
+        pl = [np.zeros(s, np.uint8) for s in d.plane_shapes()]
+        k = 0
+        while d.next(pl):
+            ok, lum = raw.read()
+            ok2, want = bgr.read()
+            assert ok and ok2
+            if lum.ndim == 2 or lum.shape[-1] == 1:
+                np.testing.assert_array_equal(lum.reshape(-1, w)[:h], pl[0])
+            u, v = (cv2.resize(c, (w, h), interpolation=cv2.INTER_LINEAR) for c in pl[1:])
+            # chroma must carry the picture's colour: far from flat, and the reconstruction close to the decoded BGR
+            assert pl[1].std() > 5 and pl[2].std() > 5
+            ycc = np.dstack([pl[0], v, u])                  # cv2's YCrCb order
+            if d.pix_fmt.startswith("yuvj"):
+                got = cv2.cvtColor(ycc, cv2.COLOR_YCrCb2BGR).astype(np.int32)
+            else:
+                yl = np.clip((pl[0].astype(np.float32) - 16) * (255 / 219), 0, 255)
+                cs = [np.clip((c.astype(np.float32) - 128) * (255 / 224) + 128, 0, 255) for c in (v, u)]
+                got = cv2.cvtColor(np.dstack([yl] + cs).round().astype(np.uint8), cv2.COLOR_YCrCb2BGR).astype(np.int32)
+            assert np.abs(got - want.astype(np.int32)).mean() < 3.0
+            swapped = cv2.cvtColor(np.dstack([pl[0], u, v]), cv2.COLOR_YCrCb2BGR).astype(np.int32)
+            assert np.abs(swapped - want.astype(np.int32)).mean() > 10.0
+            k += 1
+        assert k == n and not d.next(pl)
 
 
 def test_libvmaf_filter_string_round_trip():

@@ -280,9 +280,14 @@ def test_shard_invariance_and_batch_of_clips():
         assert batch[k]["pooled_metrics"]["vmaf"] == solo["pooled_metrics"]["vmaf"]
 
 
+def yuvio_probe(path):
+    from pqa2_b200 import yuvio
+    return yuvio.probe(path)
+
+
 def test_analyzer_on_mp4_inputs(tmp_path):
-    """The reference's real inputs are H.264/MPEG-4 MP4s (app/bookend_alignment.py:526-536): decode through cv2,
-    score the luma on the GPU, same files and dict as for raw clips."""
+    """The reference's real inputs are H.264/MPEG-4 MP4s (app/bookend_alignment.py:526-536): decode through the cv2
+    wheel's libavcodec (all planes; luma only if it cannot be driven), score on the GPU, same files and dict as for raw clips."""
     cv2 = pytest.importorskip("cv2")
     from pqa2_b200.vmaf_analyzer import VMAFAnalyzer
     w, h, n = 320, 176, 8
@@ -305,6 +310,15 @@ def test_analyzer_on_mp4_inputs(tmp_path):
     a.error_occurred.connect(errs.append)
     res = a.analyze_videos(paths[0], paths[1])
     assert not errs and res is not None and 0 < res["vmaf_score"] < 100 and len(res["raw_results"]["frames"]) == n
+    from pqa2_b200 import avdec
+    if avdec.available():
+        # all three planes reach the GPU, so the reference's FFmpeg psnr / ssim passes (app/vmaf_analyzer.py:996-1092) run
+        # on compressed inputs too: one stats line per frame, Y / U / V columns
+        assert res["psnr_log"] and res["ssim_log"] and a.get_video_metadata(paths[0])["pix_fmt"] == "yuv420p"
+        pl = open(res["psnr_log"]).read().strip().splitlines()
+        sl = open(res["ssim_log"]).read().strip().splitlines()
+        assert len(pl) == n and len(sl) == n and "mse_u:" in pl[0] and "psnr_v:" in pl[0] and " U:" in sl[0] and " V:" in sl[0]
+        assert yuvio_probe(paths[0]).decoder == "av"
     same = a.analyze_videos(paths[0], paths[0])
     assert same["vmaf_score"] >= 97.4                        # identical pair: adm2 = vif = 1 -> 97.43 at motion 0, more with motion
 
