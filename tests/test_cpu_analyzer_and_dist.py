@@ -314,3 +314,31 @@ def test_weighted_shard_ranges():
     assert engine.shard_ranges(10, 3, [1, 0, 1]) == engine.shard_ranges(10, 3)
     assert engine.shard_ranges(5, 2, [1.0, 1.0]) == [(0, 2), (2, 5)] or engine.shard_ranges(5, 2, [1.0, 1.0]) == [(0, 3), (3, 5)]
     assert D.rank_range(3600, 5, 8, weights=[24, 24, 24, 24, 36, 36, 36, 36]) == (1980, 2520)
+
+
+@pytest.mark.parametrize("bpc,w,h", [(10, 208, 120), (8, 161, 97), (12, 176, 144)])
+def test_avdec_is_bit_exact_on_raw_streams(tmp_path, bpc, w, h):
+    """A .y4m file through libavformat's yuv4mpegpipe demuxer + rawvideo decoder must hand back exactly the samples that
+    were written: pins the plane copy (line sizes, 16-bit little-endian samples, odd chroma sizes) and shows that what
+    ffmpeg would deliver for such a file equals what this repo's own raw reader delivers."""
+    from pqa2_b200 import avdec, synth
+    if not avdec.available():
+        pytest.skip("the cv2 wheel's FFmpeg libraries are not usable here")
+    n = 3
+    frames = [synth.frame_pair(6, f, w, h, bpc)[1] for f in range(n)]
+    path = str(tmp_path / "clip.y4m")
+    yuvio.write_y4m(path, frames, w, h, bpc, (24, 1))
+    info = yuvio.probe(path)
+    rd = yuvio.ClipReader(info)
+    own = rd.alloc_planes(pinned=False)
+    with avdec.AvDecoder(path) as d:
+        assert (d.width, d.height, d.bpc, d.chroma, d.codec_name) == (w, h, bpc, 420, "rawvideo") and (d.fps_num, d.fps_den) == (24, 1)
+        pl = [np.zeros(s, np.uint8 if bpc == 8 else np.uint16) for s in d.plane_shapes()]
+        for f in range(n):
+            assert d.next(pl)
+            rd.read_into(f, own)
+            for k in range(3):
+                np.testing.assert_array_equal(pl[k], frames[f][k])
+                np.testing.assert_array_equal(pl[k], own[k])
+        assert not d.next(pl)
+    rd.close()
