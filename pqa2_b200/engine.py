@@ -587,32 +587,39 @@ def _build_frames_block(rows: Rows, model: VmafModel, opt: EngineOptions, device
     opt_cols.append(("float_ms_ssim", a["float_ms_ssim"], L.FEAT_FLOAT_MS_SSIM))
     names = [c[0] for c in cols]
     table = np.stack([np.asarray(c[1], np.float64)[scored] for c in cols], axis=1).tolist() if len(scored) else []
-    extras = [(nm, np.asarray(col, np.float64)[scored].tolist(), ((valid[scored] & bit) != 0).tolist())
+    extras = [(nm, np.asarray(col, np.float64)[scored].tolist(), ((valid[scored] & bit) != 0))
               for nm, col, bit in opt_cols]
     frames = []
-    for j, i in enumerate(scored.tolist()):
-        m = dict(zip(names, table[j]))
-        for nm, vals, ok in extras:
-            if ok[j]:
-                m[nm] = vals[j]
-        frames.append({"frameNum": i, "metrics": m})
     if len(scored):
         dev = device if opt.svr_on_device else None
         vmaf = model.main.predict(feats, opt.enable_transform, opt.disable_clip, device=dev).tolist()
         boots = None
         if model.bootstrap:
             boots = np.stack([b.predict(feats, False, True, device=dev) for b in model.bootstrap], axis=1)
-        for j, fr in enumerate(frames):
-            fr["metrics"]["vmaf"] = vmaf[j]
-            if boots is not None:
-                fr["metrics"].update(_bootstrap_metrics(model, boots[j], opt))
+        # the usual clip: every optional column is present on every scored frame (or on none) -> one dict per frame
+        # straight from a row of values, keys in libvmaf's log order (model features, optional metrics, vmaf)
+        uniform = [e for e in extras if e[2].all()]
+        if boots is None and all(e[2].all() or not e[2].any() for e in extras):
+            keys = names + [e[0] for e in uniform] + ["vmaf"]
+            for i, row, ex, v in zip(scored.tolist(), table, zip(*[e[1] for e in uniform]) if uniform else [()] * len(table), vmaf):
+                frames.append({"frameNum": i, "metrics": dict(zip(keys, row + list(ex) + [v]))})
+        else:
+            oks = [e[2].tolist() for e in extras]
+            for j, i in enumerate(scored.tolist()):
+                m = dict(zip(names, table[j]))
+                for (nm, vals, _), ok in zip(extras, oks):
+                    if ok[j]:
+                        m[nm] = vals[j]
+                m["vmaf"] = vmaf[j]
+                if boots is not None:
+                    m.update(_bootstrap_metrics(model, boots[j], opt))
+                frames.append({"frameNum": i, "metrics": m})
         if pooled_out is not None and boots is None:
             # pooled_metrics straight from the columns (the per-frame dict walk of report.pooled_metrics costs ~1 ms
             # per 512 frames -- as much as a third of a launch group of GPU work)
             tab = np.asarray(table, np.float64)
             pooled = {nm: _pool_column(tab[:, k]) for k, nm in enumerate(names)}
-            for nm, vals, ok in extras:
-                okm = np.asarray(ok, bool)
+            for nm, vals, okm in extras:
                 if okm.any():
                     pooled[nm] = _pool_column(np.asarray(vals, np.float64)[okm])
             pooled["vmaf"] = _pool_column(np.asarray(vmaf, np.float64))
