@@ -246,3 +246,9 @@ class AvDecoder:
 
     def __exit__(self, *a):
         self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                              # noqa: BLE001  (interpreter shutdown)
+            pass
