@@ -60,7 +60,8 @@
 #define SPEC_DWT79_AMP { 0.62171f, 0.67234f, 0.72709f, 0.67234f }, { 0.34537f, 0.41317f, 0.49428f, 0.41317f }, \
     { 0.18004f, 0.22727f, 0.28688f, 0.22727f }, { 0.091401f, 0.11792f, 0.15214f, 0.11792f }
 /* scale-0 integer CSF factors for the default 3.0 x 1080 viewing set-up: Q21, Q21, Q23 with shifts 15, 15, 17 (L:
- * they match the 6-decimal-rounded factors, not the formula -- SURVEY.md Appendix A.4) */
+ * literals; within 1e-6 of 1 / Q(0, theta) of the model above but not its rounding, which would give 36452 and 49415 --
+ * SURVEY.md Appendix A.4, tests/test_spec_constants.py) */
 #define SPEC_ADM_S0_RF 36453, 36453, 49417
 #define SPEC_ADM_S0_RF_SHIFT 15, 15, 17
 #define SPEC_ADM_S0_RF_ROUND 16384, 16384, 65536

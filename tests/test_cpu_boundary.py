@@ -71,6 +71,36 @@ def test_svr_host_matches_oracle_bit_exact():
         assert got[i] == oracle.svr_predict(feats[i], m.slopes, m.intercepts, m.sv, m.coef, m.gamma, m.rho)
 
 
+@pytest.mark.parametrize("name", ["vmaf_v0.6.1", "vmaf_float_v0.6.1", "vmaf_4k_v0.6.1", "vmaf_v0.6.1neg", "vmaf_b_v0.6.3"])
+def test_svr_against_libsvm_itself(name):
+    """A THIRD-PARTY pin of the fusion stage: scikit-learn vendors libsvm, so its NuSVR.predict runs libsvm's own
+    svm_predict.  The fitted state of a dummy NuSVR is replaced by the parameters of the reference's model file (support
+    vectors, coefficients, rho, gamma -- `models/*.json`, libsvm text under "model"), and libsvm's prediction on the
+    normalised features, de-normalised as libvmaf's predict.c does, must equal the C oracle's and the C-ABI library's
+    host evaluation (every support vector, every bootstrap model)."""
+    svm = pytest.importorskip("sklearn.svm")
+    import oracle
+    vm = M.resolve_model(name)
+    rng = np.random.default_rng(7)
+    feats = rng.uniform([0.3, 0, 0.1, 0.3, 0.4, 0.5], [1.0, 20, 1, 1, 1, 1], size=(48, 6))
+    for m in [vm.main] + list(vm.bootstrap)[:3]:
+        n_sv, nf = m.sv.shape
+        s = svm.NuSVR(kernel="rbf", gamma=m.gamma).fit(rng.random((max(50, n_sv), nf)), rng.random(max(50, n_sv)))
+        s.support_vectors_ = np.ascontiguousarray(m.sv, np.float64)
+        s.support_ = np.arange(n_sv, dtype=np.int32)
+        s._n_support = np.array([n_sv, 0], dtype=np.int32)
+        s.dual_coef_ = s._dual_coef_ = np.ascontiguousarray(m.coef.reshape(1, -1), np.float64)
+        s.intercept_ = s._intercept_ = np.array([-m.rho])            # libsvm: sum - rho
+        s._gamma = m.gamma
+        s.shape_fit_ = (n_sv, nf)
+        want = (s.predict(feats * m.slopes[1:] + m.intercepts[1:]) - m.intercepts[0]) / m.slopes[0]
+        got_c = m.predict(feats, disable_clip=True)
+        got_o = np.array([oracle.svr_predict(f, m.slopes, m.intercepts, m.sv, m.coef, m.gamma, m.rho) for f in feats])
+        np.testing.assert_allclose(got_o, want, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(got_c, want, rtol=0, atol=1e-11)
+        assert want.std() > 5                                        # un-clipped scores of random feature vectors: spread out
+
+
 def test_model_files():
     names = M.available_models()
     for n in ["vmaf_v0.6.1", "vmaf_v0.6.1neg", "vmaf_4k_v0.6.1", "vmaf_4k_v0.6.1neg", "vmaf_b_v0.6.3",
