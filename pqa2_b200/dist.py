@@ -91,20 +91,31 @@ def analyze_distributed(src, model, opt: engine.EngineOptions | None = None, dev
     n = src.nb_frames
     start, end = rank_range(n, rank, world, weights=weights)
     mask = engine.feature_mask(model, opt)
-    if end <= start:
-        mine = {}
-    elif shard_fn is not None:
-        mine = shard_fn(src, model, opt, device, start, end, mask)
-    else:
-        mine = _default_shard_fn(src, model, opt, device, start, end, mask, session)
+    failure = None
+    try:
+        if end <= start:
+            mine = {}
+        elif shard_fn is not None:
+            mine = shard_fn(src, model, opt, device, start, end, mask)
+        else:
+            mine = _default_shard_fn(src, model, opt, device, start, end, mask, session)
+    except Exception as e:                # noqa: BLE001
+        # every rank must still reach the gather (a rank that raised before it would leave the others waiting for ever):
+        # the failure travels as this rank's part, rank 0 reports it, this rank re-raises its own exception afterwards
+        failure, mine = e, ("failed", rank, f"{type(e).__name__}: {e}")
     if world > 1:
         import torch.distributed as dist
         gathered = [None] * world if rank == 0 else None
         dist.gather_object(mine, gathered, dst=0, group=group)
     else:
         gathered = [mine]
+    if failure is not None:
+        raise failure
     if rank != 0:
         return None
+    bad = [p for p in gathered if isinstance(p, tuple) and p and p[0] == "failed"]
+    if bad:
+        raise RuntimeError("; ".join(f"rank {r}: {msg}" for _, r, msg in bad))
     if all(isinstance(p, tuple) or not p for p in gathered):
         rows = engine.Rows(n)
         for part in gathered:

@@ -146,6 +146,46 @@ def _worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
+def _failing_shard(src, model, opt, device, start, end, mask):
+    if start > 0:
+        raise ValueError("decoder gave up")
+    return _fake_shard(src, model, opt, device, start, end, mask)
+
+
+def _worker_one_rank_fails(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        try:
+            D.analyze_distributed(_FakeClip(9), M.resolve_model("vmaf_v0.6.1"), engine.EngineOptions(svr_on_device=False),
+                                  shard_fn=_failing_shard)
+            q.put((rank, "returned"))
+        except Exception as e:            # noqa: BLE001
+            q.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_a_failing_rank_does_not_hang_the_gather():
+    """A shard that raises on one rank: every rank still reaches the gather, rank 0 reports which rank failed and why,
+    the failing rank re-raises its own exception -- nobody waits for ever."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_one_rank_fails, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert got[1] == "ValueError: decoder gave up"
+    assert got[0].startswith("RuntimeError: rank 1: ValueError: decoder gave up")
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
