@@ -7,6 +7,6 @@ import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l); k=d.get('kernels',{})
-        print('[$lib]', round(d['value'],1), {n: round(v['ms_per_launch'],4) for n,v in k.items() if v['ms_per_launch']>0.2})
+        print('[$lib]', round(d['value'],1), {n: round(v['ms_per_launch'],4) for n,v in k.items() if 'adm' in n})
 "
 done
