@@ -19,11 +19,17 @@ struct bv_model {
     // Device mirrors: one per GPU, created on first use under `mu` and never freed before bv_model_free, so
     // a VmafModel shared by one worker thread per GPU (engine.analyze_batch, sweep.run_sweep) is safe: a thread on
     // device A never sees (or frees) the buffers of device B.
+    // Each mirror also owns a stream and grow-only scratch for the feature rows and the scores: a predict call must not
+    // cudaMalloc / cudaFree (cudaFree waits for EVERY stream of the device, i.e. for the extractor kernels still draining
+    // while the host already scores the first part of a clip -- engine.analyze builds those frames during the drain).
     struct Mirror {
         int dev = -1;
         double *d_sv = nullptr, *d_coef = nullptr, *d_slopes = nullptr, *d_intercepts = nullptr;
+        double *d_feat = nullptr, *d_out = nullptr;
+        int64_t cap = 0;
+        cudaStream_t st = nullptr;
     };
-    std::mutex mu;
+    std::mutex mu;                       // held for a whole bv_predict_device call (they take ~0.1 ms)
     std::vector<Mirror> mirrors;
 };
 
@@ -78,6 +84,8 @@ void bv_model_free(bv_model *m)
     for (const bv_model::Mirror &r : m->mirrors) {
         if (cudaSetDevice(r.dev) != cudaSuccess) { cudaGetLastError(); continue; }
         cudaFree(r.d_sv); cudaFree(r.d_coef); cudaFree(r.d_slopes); cudaFree(r.d_intercepts);
+        cudaFree(r.d_feat); cudaFree(r.d_out);
+        if (r.st) cudaStreamDestroy(r.st);
     }
     delete m;
 }
@@ -110,39 +118,43 @@ int bv_predict_device(const bv_model *cm, int device, const double *feat, int64_
     if (!m || !feat || !out || n < 0) return BV_ERR_ARG;
     if (n == 0) return 0;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return BV_ERR_CUDA; }
-    bv_model::Mirror mir;
-    {
-        std::lock_guard<std::mutex> lock(m->mu);
-        for (const bv_model::Mirror &r : m->mirrors) if (r.dev == device) mir = r;
-        if (mir.dev < 0) {
-            bv_model::Mirror r;
-            const size_t nsv = m->sv.size() * sizeof(double), ncoef = m->coef.size() * sizeof(double),
-                         nsl = m->slopes.size() * sizeof(double);
-            if (cudaMalloc(&r.d_sv, nsv) || cudaMalloc(&r.d_coef, ncoef) || cudaMalloc(&r.d_slopes, nsl) ||
-                cudaMalloc(&r.d_intercepts, nsl) ||
-                cudaMemcpy(r.d_sv, m->sv.data(), nsv, cudaMemcpyHostToDevice) ||
-                cudaMemcpy(r.d_coef, m->coef.data(), ncoef, cudaMemcpyHostToDevice) ||
-                cudaMemcpy(r.d_slopes, m->slopes.data(), nsl, cudaMemcpyHostToDevice) ||
-                cudaMemcpy(r.d_intercepts, m->intercepts.data(), nsl, cudaMemcpyHostToDevice)) {
-                cudaGetLastError();
-                cudaFree(r.d_sv); cudaFree(r.d_coef); cudaFree(r.d_slopes); cudaFree(r.d_intercepts);
-                return BV_ERR_CUDA;
-            }
-            r.dev = device;
-            m->mirrors.push_back(r);
-            mir = r;
+    std::lock_guard<std::mutex> lock(m->mu);
+    bv_model::Mirror *mir = nullptr;
+    for (bv_model::Mirror &r : m->mirrors) if (r.dev == device) mir = &r;
+    if (!mir) {
+        bv_model::Mirror r;
+        const size_t nsv = m->sv.size() * sizeof(double), ncoef = m->coef.size() * sizeof(double),
+                     nsl = m->slopes.size() * sizeof(double);
+        if (cudaMalloc(&r.d_sv, nsv) || cudaMalloc(&r.d_coef, ncoef) || cudaMalloc(&r.d_slopes, nsl) ||
+            cudaMalloc(&r.d_intercepts, nsl) ||
+            cudaMemcpy(r.d_sv, m->sv.data(), nsv, cudaMemcpyHostToDevice) ||
+            cudaMemcpy(r.d_coef, m->coef.data(), ncoef, cudaMemcpyHostToDevice) ||
+            cudaMemcpy(r.d_slopes, m->slopes.data(), nsl, cudaMemcpyHostToDevice) ||
+            cudaMemcpy(r.d_intercepts, m->intercepts.data(), nsl, cudaMemcpyHostToDevice) ||
+            cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking)) {
+            cudaGetLastError();
+            cudaFree(r.d_sv); cudaFree(r.d_coef); cudaFree(r.d_slopes); cudaFree(r.d_intercepts);
+            return BV_ERR_CUDA;
         }
+        r.dev = device;
+        m->mirrors.push_back(r);
+        mir = &m->mirrors.back();
     }
-    double *d_feat = nullptr, *d_out = nullptr;
-    if (cudaMalloc(&d_feat, sizeof(double) * n * m->n_feat) || cudaMalloc(&d_out, sizeof(double) * n)) {
-        cudaGetLastError(); cudaFree(d_feat); return BV_ERR_CUDA;
+    if (n > mir->cap) {                  // rare: the first clip, or a longer one than any before
+        const int64_t cap = n > 2 * mir->cap ? n : 2 * mir->cap;
+        cudaFree(mir->d_feat); cudaFree(mir->d_out);
+        mir->d_feat = mir->d_out = nullptr;
+        mir->cap = 0;
+        if (cudaMalloc(&mir->d_feat, sizeof(double) * cap * m->n_feat) || cudaMalloc(&mir->d_out, sizeof(double) * cap)) {
+            cudaGetLastError(); cudaFree(mir->d_feat); mir->d_feat = nullptr; return BV_ERR_CUDA;
+        }
+        mir->cap = cap;
     }
-    cudaMemcpy(d_feat, feat, sizeof(double) * n * m->n_feat, cudaMemcpyHostToDevice);
-    bv_launch_svr(d_feat, m->n_feat, mir.d_slopes, mir.d_intercepts, mir.d_sv, mir.d_coef, m->n_sv, m->gamma, m->rho,
-                  d_out, n, 0);
-    cudaError_t e = cudaMemcpy(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost);
-    cudaFree(d_feat); cudaFree(d_out);
-    if (e != cudaSuccess) { cudaGetLastError(); return BV_ERR_CUDA; }
+    cudaMemcpyAsync(mir->d_feat, feat, sizeof(double) * n * m->n_feat, cudaMemcpyHostToDevice, mir->st);
+    bv_launch_svr(mir->d_feat, m->n_feat, mir->d_slopes, mir->d_intercepts, mir->d_sv, mir->d_coef, m->n_sv, m->gamma,
+                  m->rho, mir->d_out, n, mir->st);
+    cudaMemcpyAsync(out, mir->d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, mir->st);
+    if (cudaStreamSynchronize(mir->st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return BV_ERR_CUDA;
     for (int64_t r = 0; r < n; ++r) out[r] = post(m, out[r], flags);
     return 0;
 }

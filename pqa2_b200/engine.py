@@ -287,6 +287,7 @@ def shard_ranges(n_frames: int, n_shards: int, weights=None):
 
 
 _FIRST_KICK = 8
+_EARLY_MIN = 64            # rows worth building ahead of the drain (below that the tail is short anyway)
 
 
 class _Cancelled(Exception):
@@ -295,7 +296,7 @@ class _Cancelled(Exception):
 
 def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: int, start: int, end: int,
                mask: int, rows: list, progress, cancel: threading.Event, errors: list, ctx_holder: list,
-               session: "Engine | None" = None, shard: int = 0, lead_in: bool | None = None):
+               session: "Engine | None" = None, shard: int = 0, lead_in: bool | None = None, early=None):
     handle = None
     fx = None
     pre = None
@@ -375,12 +376,26 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
                 fx.kick()
             if progress:
                 progress(1)
+        got = 0
+        if early is not None and isinstance(rows, Rows) and ordinal:
+            # Up to three launch groups are still on the GPU when the last frame has been submitted (a few ms of work).
+            # Start the last (partial) group now and hand every row that is already complete to `early`, which builds
+            # those frames' log entries while the GPU drains -- instead of doing all of it after the drain.
+            fx.kick()
+            got = min(int(fx.frames_done()), ordinal)
+            if got - lead >= _EARLY_MIN:
+                out = np.ctypeslib.as_array(fx.fetch(0, got))
+                rows.put(out["frame_index"][lead:got], out[lead:got])
+                early(int(out["frame_index"][got - 1]) + 1)
+            else:
+                got = 0
         fx.flush()
-        out = np.ctypeslib.as_array(fx.fetch(0, ordinal))       # structured view of the bv_frame_features records
+        out = np.ctypeslib.as_array(fx.fetch(got, ordinal - got))       # structured view of the bv_frame_features records
+        skip = max(lead - got, 0)
         if isinstance(rows, Rows):
-            rows.put(out["frame_index"][lead:ordinal], out[lead:ordinal])
+            rows.put(out["frame_index"][skip:], out[skip:])
         else:
-            for k in range(lead, ordinal):
+            for k in range(skip, len(out)):
                 rows[int(out["frame_index"][k])] = RowView(out, k)
     except _Cancelled:
         errors.append(("cancelled", None))
@@ -536,16 +551,18 @@ def _pool_column(col: np.ndarray) -> dict:
 
 
 def _build_frames_block(rows: Rows, model: VmafModel, opt: EngineOptions, device: int | None,
-                        pooled_out: dict | None = None) -> list:
+                        pooled_out: dict | None = None, clip_start: bool = True, cols_out: dict | None = None) -> list:
     """build_frames() on a Rows block: whole columns at a time (the per-row dict path costs ~50 us/frame in
-    Python, which at several thousand frames/s is as much as the GPU work itself)."""
+    Python, which at several thousand frames/s is as much as the GPU work itself).  ``clip_start=False``: the block
+    continues a clip (its first row keeps its motion); ``cols_out`` receives the numeric columns of the scored frames
+    (name -> (values, present mask or None)) so that a caller who builds a clip in two blocks can pool over both."""
     a = rows.arr
     is_f = model.is_float
     pre = "" if is_f else "integer_"
     vs, as_ = _egl_suffix(model.vif_enhn_gain_limit), _egl_suffix(model.adm_enhn_gain_limit)
     n = len(a)
     motion = np.array(a["f_motion"] if is_f else a["motion"], np.float64)
-    if n:
+    if n and clip_start:
         motion[0] = 0.0
     motion2 = motion.copy()
     if n > 1:
@@ -577,7 +594,7 @@ def _build_frames_block(rows: Rows, model: VmafModel, opt: EngineOptions, device
         opt_cols.append(("psnr_cr", a["psnr_cr"], L.FEAT_PSNR_UV))
     if opt.float_motion and not is_f:
         fm = np.array(a["f_motion"], np.float64)
-        if n:
+        if n and clip_start:
             fm[0] = 0.0
         fm2 = fm.copy()
         if n > 1:
@@ -614,32 +631,54 @@ def _build_frames_block(rows: Rows, model: VmafModel, opt: EngineOptions, device
                 if boots is not None:
                     m.update(_bootstrap_metrics(model, boots[j], opt))
                 frames.append({"frameNum": i, "metrics": m})
-        if pooled_out is not None and boots is None:
+        if (pooled_out is not None or cols_out is not None) and boots is None:
             # pooled_metrics straight from the columns (the per-frame dict walk of report.pooled_metrics costs ~1 ms
             # per 512 frames -- as much as a third of a launch group of GPU work)
             tab = np.asarray(table, np.float64)
-            pooled = {nm: _pool_column(tab[:, k]) for k, nm in enumerate(names)}
+            cols_ = {nm: (tab[:, k], None) for k, nm in enumerate(names)}
             for nm, vals, okm in extras:
-                if okm.any():
-                    pooled[nm] = _pool_column(np.asarray(vals, np.float64)[okm])
-            pooled["vmaf"] = _pool_column(np.asarray(vmaf, np.float64))
-            pooled_out["pooled"] = pooled
+                cols_[nm] = (np.asarray(vals, np.float64), okm)
+            cols_["vmaf"] = (np.asarray(vmaf, np.float64), None)
+            if cols_out is not None:
+                cols_out.update(cols_)
+            if pooled_out is not None:
+                pooled_out["pooled"] = _pool_columns([cols_])
     return frames
+
+
+def _pool_columns(parts: list) -> dict:
+    """Pooled metrics over the concatenation of column sets (one per block of a clip, in clip order)."""
+    pooled = {}
+    for nm in parts[0]:
+        vals = np.concatenate([p[nm][0] for p in parts])
+        if parts[0][nm][1] is not None:
+            ok = np.concatenate([p[nm][1] for p in parts])
+            if not ok.any():
+                continue
+            vals = vals[ok]
+        pooled[nm] = _pool_column(vals)
+    return pooled
+
+
+class _NoGc:
+    """Two dicts per frame: with the cyclic collector on, a long clip triggers full collections in the middle of the build
+    (measured: 10 ms .. 0.5 s for 3600 frames, run to run); nothing built there can be cyclic garbage."""
+
+    def __enter__(self):
+        import gc
+        self._gc, self._was_on = gc, gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *a):
+        if self._was_on:
+            self._gc.enable()
 
 
 def build_frames(rows, model: VmafModel, opt: EngineOptions, device: int | None, pooled_out: dict | None = None) -> list:
     """Per-frame feature rows -> libvmaf 'frames' list (metric names of SURVEY.md Appendix A.8)."""
     if isinstance(rows, Rows):
-        # two dicts per frame: with the cyclic collector on, a long clip triggers full collections in the middle of the
-        # build (measured: 10 ms .. 0.5 s for 3600 frames, run to run); nothing built here can be cyclic garbage
-        import gc
-        was_on = gc.isenabled()
-        gc.disable()
-        try:
+        with _NoGc():
             return _build_frames_block(rows, model, opt, device, pooled_out)
-        finally:
-            if was_on:
-                gc.enable()
     is_f = model.is_float
     pre = "" if is_f else "integer_"
     vs, as_ = _egl_suffix(model.vif_enhn_gain_limit), _egl_suffix(model.adm_enhn_gain_limit)
@@ -760,6 +799,18 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
     holders: list = []
     t0 = time.perf_counter()
     threads = []
+    head: dict = {}
+
+    def build_early(hi):
+        """Runs on the shard thread while the GPU finishes its last launch groups: log entries of the frames [first, hi - 1)
+        from the rows that are complete already (frame hi - 1 waits for its successor's motion)."""
+        cols: dict = {}
+        with _NoGc():
+            frs = _build_frames_block(rows[first:hi], model, opt, devices[0], None, True, cols)
+        keep = sum(1 for fr in frs if fr["frameNum"] < hi - 1 - first)
+        if keep and cols:
+            head.update(frames=frs[:keep], upto=hi - 1,
+                        cols={nm: (v[:keep], None if ok is None else ok[:keep]) for nm, (v, ok) in cols.items()})
     # Long clips on several GPUs: the devices pull chunks of `dynamic_chunk` frames from a shared counter instead of
     # each getting one fixed share.  The GPUs of one box do not see the same host-to-device bandwidth under load (four
     # of the eight B200s share a host bridge: ~24 vs ~36 GB/s each, tools/h2d_concurrent.py), and with equal shares the
@@ -786,13 +837,14 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
             th.start()
             threads.append(th)
     else:
-        for k, (dev, (a, b)) in enumerate(zip(devices, ranges)):
-            if b <= a:
-                continue
+        live = [(k, dev, a, b) for k, (dev, (a, b)) in enumerate(zip(devices, ranges)) if b > a]
+        for k, dev, a, b in live:
             # a frame_range is scored as libvmaf would score the trimmed clip: its first frame has no predecessor
             # (motion = 0), so only the shards after the first one get a lead-in frame
             th = threading.Thread(target=_run_shard, args=(src, model, opt, dev, a, b, mask, rows, progress, cancel,
-                                                           errors, holders, session, k, a > first), daemon=True)
+                                                           errors, holders, session, k, a > first,
+                                                           build_early if len(live) == 1 and not model.bootstrap else None),
+                                  daemon=True)
             th.start()
             threads.append(th)
     for th in threads:
@@ -812,7 +864,21 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
             raise EOFError("no frame could be decoded")
     rows_used = rows[first:last]
     pooled_out: dict = {}
-    frames = build_frames(rows_used, model, opt, devices[0], pooled_out)
+    if head and head["upto"] < last:
+        # the rest of the clip, continuing where the early block stopped; pooling runs over both blocks' columns
+        s0 = head["upto"]
+        cols: dict = {}
+        with _NoGc():
+            tail = _build_frames_block(rows[s0:last], model, opt, devices[0], None, False, cols)
+        for fr in tail:
+            fr["frameNum"] += s0 - first
+        frames = head["frames"] + tail
+        if cols:
+            pooled_out["pooled"] = _pool_columns([head["cols"], cols])
+        elif not tail:
+            pooled_out["pooled"] = _pool_columns([head["cols"]])
+    else:
+        frames = build_frames(rows_used, model, opt, devices[0], pooled_out)
     for fr in frames:
         fr["frameNum"] += first
     dt = time.perf_counter() - t0

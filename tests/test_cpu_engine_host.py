@@ -3,6 +3,8 @@
 lead-in, n_subsample), launch-group kicks, shard ranges with lead-in frames, the motion2 rule over shard borders, the SVR
 (host libsvm path of the C library), pooling -- against a single-shard run and against direct arithmetic.
 Reference behaviour restated: libvmaf frame flow as reached from app/vmaf_analyzer.py:417."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -44,7 +46,20 @@ class FakeExtractor:
     def close(self):
         pass
 
+    in_flight = 40           # frames still "on the GPU" when the last one has been submitted (the drain the host overlaps)
+
+    def frames_done(self):
+        return max(0, len(self.frames) - self.in_flight)
+
     def fetch(self, first=0, count=None):
+        count = len(self.frames) - first if count is None else count
+        full = self._all()
+        arr = (L.BvFrameFeatures * count)()
+        for k in range(count):
+            C.memmove(C.byref(arr[k]), C.byref(full[first + k]), C.sizeof(L.BvFrameFeatures))
+        return arr
+
+    def _all(self):
         arr = (L.BvFrameFeatures * len(self.frames))()
         prev = None
         for k, (idx, content, flags) in enumerate(self.frames):
@@ -105,7 +120,8 @@ def test_flags_kicks_and_shards(fake):
     assert [i for i, _, _ in fx.frames] == list(range(n))
     assert fx.frames[0][2] & L.FRAME_FIRST and not any(fl & L.FRAME_FIRST for _, _, fl in fx.frames[1:])
     assert not any(fl & (L.FRAME_LEAD_IN | L.FRAME_SKIP_SPATIAL) for _, _, fl in fx.frames)
-    assert fx.kicks == [8]                                   # a short first group; no tail split at <= 1440p (32-frame groups)
+    assert fx.kicks == [8, n]                                # a short first group; no tail split at <= 1440p (32-frame groups);
+                                                             # the last partial group is started before the early hand-over
 
     fake.instances.clear()
     three = engine.analyze(Clip(n), model, _opt(psnr=True, devices=(0, 0, 0)))
@@ -143,8 +159,34 @@ def test_tail_split_only_for_reduced_group_sizes(fake, monkeypatch):
     model = M.resolve_model("vmaf_v0.6.1")
     engine.analyze(Clip(100), model, _opt(batch_frames=16))
     (fx,) = fake.instances
-    # first kick after 8 frames, then when 8 and 4 frames are left (2160p-style 16-frame groups)
-    assert fx.kicks == [8, 92, 96]
+    # first kick after 8 frames, then when 8 and 4 frames are left (2160p-style 16-frame groups), then the last partial
+    # group before the rows that are already complete are handed over
+    assert fx.kicks == [8, 92, 96, 100]
+
+
+@pytest.mark.parametrize("n,sub,rng", [(200, 1, None), (131, 3, None), (300, 1, (17, 260)), (105, 1, None), (90, 1, None)])
+def test_frames_built_during_the_drain_equal_the_one_pass_build(fake, monkeypatch, n, sub, rng):
+    """A single-shard analysis hands the rows that are complete when the last frame has been submitted to the frame
+    builder while the GPU drains (engine.analyze `build_early`), and builds the rest afterwards: frames, motion2 across
+    the seam, the optional columns and the pooled report must equal the one-pass build (three shards never take the
+    early path), also with n_subsample and a frame range; too few complete rows -> the one-pass build."""
+    model = M.resolve_model("vmaf_v0.6.1")
+    calls = []
+    real = engine._build_frames_block
+    monkeypatch.setattr(engine, "_build_frames_block", lambda *a, **k: (calls.append(len(a[0])), real(*a, **k))[1])
+    one = engine.analyze(Clip(n), model, _opt(psnr=True, n_subsample=sub, devices=(0,)), frame_range=rng)
+    span = n if rng is None else rng[1] - rng[0]
+    early = span - FakeExtractor.in_flight >= engine._EARLY_MIN
+    assert len(calls) == (2 if early else 1)
+    if early:
+        assert calls[0] == span - FakeExtractor.in_flight and calls[1] == FakeExtractor.in_flight + 1
+    fake.instances.clear()
+    calls.clear()
+    three = engine.analyze(Clip(n), model, _opt(psnr=True, n_subsample=sub, devices=(0, 0, 0)), frame_range=rng)
+    assert len(calls) == 1
+    assert one["frames"] == three["frames"] and one["pooled_metrics"] == three["pooled_metrics"]
+    assert [fr["frameNum"] for fr in one["frames"]] == [i for i in range(*(rng or (0, n))) if i % sub == 0]
+    assert list(one["pooled_metrics"]) == list(three["pooled_metrics"]) and "psnr_y" in one["pooled_metrics"]
 
 
 def test_frame_range_and_empty_clip(fake):
