@@ -139,27 +139,50 @@ def analyze_distributed(src, model, opt: engine.EngineOptions | None = None, dev
 
 
 def analyze_batch_distributed(clips: list, model, opt: engine.EngineOptions | None = None, device: int = 0, group=None,
-                              session: "engine.Engine | None" = None, summarize=None):
+                              session: "engine.Engine | None" = None, summarize=None, concurrency: int = 2):
     """Many clips over the ranks (BASELINE.json configs[4]; the one-process-per-GPU twin of engine.analyze_batch):
-    whole clips are the unit, clip k runs on rank ``k % world`` through that rank's session, and one small summary per
-    clip -- by default its pooled report -- is gathered on rank 0, in input order.  No lead-in frames, no collective on
-    the data path.  Returns the list on rank 0, None elsewhere; a failed clip yields ``{"error": str}``."""
+    whole clips are the unit, clip k runs on rank ``k % world``, and one small summary per clip -- by default its
+    pooled report -- is gathered on rank 0, in input order.  No lead-in frames, no collective on the data path.
+
+    ``concurrency`` clips are in flight on this rank's GPU at once, each through its own session (own CUDA context,
+    streams and pinned ring): a clip's pipeline fill and its drain + read-back + scoring leave the GPU partly idle for a
+    few ms, which for clips of a few hundred frames is 10-15 % of the clip; a second clip fills those gaps.  ``session``
+    may be one Engine or a list of them (one per worker) that outlive the call; missing ones are created and closed here.
+    Returns the list on rank 0, None elsewhere; a failed clip yields ``{"error": str}``."""
     from dataclasses import replace
     opt = replace(opt or engine.EngineOptions(), devices=(device,))
     rank, world = _world(group)
     summarize = summarize or (lambda log: {k: v for k, v in log.items() if k not in ("frames", "rows")})
-    own = session is None
-    sess = session or engine.Engine()
-    mine = {}
-    try:
-        for k in range(rank, len(clips), world):
-            try:
-                mine[k] = summarize(sess.analyze(clips[k], model, opt))
-            except Exception as e:            # noqa: BLE001  (the reference's per-clip error convention)
-                mine[k] = {"error": str(e)}
-    finally:
-        if own:
-            sess.close()
+    todo = list(range(rank, len(clips), world))
+    mine: dict = {}
+    lock = threading.Lock()
+
+    def worker(sess, own):
+        try:
+            while True:
+                with lock:
+                    if not todo:
+                        return
+                    k = todo.pop(0)
+                try:
+                    out = summarize(sess.analyze(clips[k], model, opt))
+                except Exception as e:            # noqa: BLE001  (the reference's per-clip error convention)
+                    out = {"error": str(e)}
+                with lock:
+                    mine[k] = out
+        finally:
+            if own:
+                sess.close()
+
+    given = list(session) if isinstance(session, (list, tuple)) else ([session] if session is not None else [])
+    n_workers = max(1, min(int(concurrency), max(len(todo), 1)))
+    sessions = [(given[w], False) if w < len(given) else (engine.Engine(), True) for w in range(n_workers)]
+    threads = [threading.Thread(target=worker, args=sw, daemon=True) for sw in sessions[1:]]
+    for t in threads:
+        t.start()
+    worker(*sessions[0])
+    for t in threads:
+        t.join()
     if world > 1:
         import torch.distributed as dist
         gathered = [None] * world if rank == 0 else None

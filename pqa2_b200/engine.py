@@ -889,24 +889,31 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
 
 
 def analyze_batch(clips: list, model: VmafModel, opt: EngineOptions | None = None, devices=None,
-                  progress_cb=None) -> list:
+                  progress_cb=None, concurrency: int = 2) -> list:
     """Many clips over many GPUs (BASELINE.json configs[4]: a sweep of 64 1080p clip pairs on 8 B200).
 
-    Whole clips are the unit here -- no lead-in frames, no cross-GPU state: clip k runs on
-    ``devices[k % len(devices)]`` through that device's session (one context per GPU, reused for every
-    clip of the same geometry).  Returns one libvmaf log dict per clip, in input order; a clip that
+    Whole clips are the unit here -- no lead-in frames, no cross-GPU state: every GPU has ``concurrency`` workers, each
+    with its own session (one context, reused for every clip of the same geometry), which take the next clip from a
+    shared list; two clips in flight per GPU fill the few ms a single clip leaves idle while its pipeline fills and while
+    its last launch groups drain and are scored.  Returns one libvmaf log dict per clip, in input order; a clip that
     fails yields ``{"error": str}`` in its slot (the reference's per-clip error convention)."""
     opt = opt or EngineOptions()
     devices = list(devices if devices is not None else opt.devices) or [0]
     results: list = [None] * len(clips)
     lock = threading.Lock()
     done = [0]
+    nxt = [0]
 
-    def worker(slot: int, dev: int):
+    def worker(dev: int):
         from dataclasses import replace
         o = replace(opt, devices=(dev,))
         with Engine() as sess:
-            for k in range(slot, len(clips), len(devices)):
+            while True:
+                with lock:
+                    k = nxt[0]
+                    nxt[0] += 1
+                if k >= len(clips):
+                    return
                 try:
                     results[k] = sess.analyze(clips[k], model, o)
                 except Exception as e:            # noqa: BLE001
@@ -917,7 +924,9 @@ def analyze_batch(clips: list, model: VmafModel, opt: EngineOptions | None = Non
                         d = done[0]
                     progress_cb(d, len(clips))
 
-    threads = [threading.Thread(target=worker, args=(i, d), daemon=True) for i, d in enumerate(devices)]
+    per_dev = max(1, int(concurrency))
+    threads = [threading.Thread(target=worker, args=(d,), daemon=True) for _ in range(per_dev) for d in devices]
+    threads = threads[:max(1, len(clips))]
     for t in threads:
         t.start()
     for t in threads:

@@ -114,6 +114,9 @@ class _FakeSession:
     def __init__(self, rank):
         self.rank = rank
 
+    def close(self):
+        pass
+
     def analyze(self, clip, model, opt):
         if clip.nb_frames == 13:
             raise RuntimeError("bad clip")
@@ -135,7 +138,12 @@ def _worker(rank, world, port, n, q):
         # whole clips dealt over the ranks (configs[4]): summaries come back on rank 0 in input order, a failing clip
         # fills its own slot only
         clips = [_FakeClip(k) for k in (11, 12, 13, 14, 15)]
-        batch = D.analyze_batch_distributed(clips, model, opt, device=rank, session=_FakeSession(rank))
+        batch = D.analyze_batch_distributed(clips, model, opt, device=rank, session=_FakeSession(rank), concurrency=1)
+        # two clips in flight per rank, each worker with a session of its own: same summaries, same slots
+        made = []
+        engine.Engine = lambda: (made.append(1), _FakeSession(rank))[1]
+        batch2 = D.analyze_batch_distributed(clips, model, opt, device=rank, concurrency=2)
+        assert len(made) == 2 and (batch2 == batch if rank == 0 else batch2 is None)
         if rank == 0:
             assert [b.get("n_frames") for b in batch] == [11, 12, None, 14, 15] and "bad clip" in batch[2]["error"]
             assert [b["rank"] for b in batch if "rank" in b] == [0, 1, 1, 0]
