@@ -8,7 +8,8 @@ A *step* is one pass of the hot path over one batch of `frames_per_step` synthet
 pairs per GPU (weak scaling: frame chunks are independent, there is no data-path collective --
 SURVEY.md §8e).  `value` = frame pairs per second over all GPUs with the clips resident in HBM;
 `e2e` = the same through the public engine call (pqa2_b200.engine.analyze) from pinned HOST frames,
-host->device copies and the feature read-back inside the timed region.
+host->device copies and the feature read-back inside the timed region: ONE call over the K steps' frames (20 x 512 = the
+10k-frame clip of configs[1]); `e2e.one_call_per_step` is the same work as K separate 512-frame clips.
 
 Headline workload (identical at every N): configs[1].  Next to it, in the same JSON line:
   workloads      (N = 1)  the integer v0.6.1 configurations BASELINE's metric names -- 1080p-int (configs[0] shape)
@@ -516,27 +517,37 @@ def measure_workload(cx: Ctx, wname: str, wl: dict, pool: Pool, steps: int, warm
     # ---- end to end through the public engine call: pinned host frames in, scores out
     e2e = None
     if with_e2e:
-        # one engine session (contexts stay alive between clips, as in a sweep of many clips); a step = one
-        # engine.analyze call over fps_step host frames: H2D of every plane the enabled features read, kernels, D2H of
-        # the feature rows, SVR fusion and pooling -- all inside the timed region.
-        k_e2e = max(1, min(steps, 10))
+        # one engine session; the timed region is ONE engine.analyze call over the K steps' frames -- the call a user makes
+        # for a clip of that length (configs[1] is one 10k-frame pair: 20 steps x 512 frames) -- with, for every step's
+        # frames, H2D of every plane the enabled features read, the kernels and D2H of the feature rows as the launch groups
+        # complete, and SVR fusion + log entries + pooling of the whole clip before the call returns.
+        k_e2e = max(1, steps)
         with engine.Engine() as sess:
             for _ in range(2):
                 sess.analyze(pool.clip(fps_step), model, opt)                    # warm-up (allocations, first launches)
             cx.barrier()
             t0 = time.perf_counter()
-            for _ in range(k_e2e):
-                res = sess.analyze(pool.clip(fps_step), model, opt)
+            res = sess.analyze(pool.clip(fps_step * k_e2e), model, opt)
             dt = time.perf_counter() - t0
-        dt = cx.max_over_ranks(dt)
+            dt = cx.max_over_ranks(dt)
+            # the same frames as separate short clips (one call per step): what pipeline fill, drain and scoring cost per call
+            k_short = max(1, min(steps, 10))
+            cx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_short):
+                res_s = sess.analyze(pool.clip(fps_step), model, opt)
+            dt_s = cx.max_over_ranks(time.perf_counter() - t0)
         n_e2e = fps_step * k_e2e
         e2e = {"value": n_e2e * world / dt, "unit": "frames/s",
                "h2d_bytes_per_step": int(2 * frame_bytes * fps_step),
                "d2h_bytes_per_step": int((L.BV_RAW_WORDS * 8 + 64 * 8) * fps_step + 8 * fps_step),
-               "frames": n_e2e, "steps": k_e2e, "ms_per_step": 1000.0 * dt / k_e2e,
-               "timer": "host wall clock around K engine.analyze calls (pinned host frames -> H2D, kernels, feature D2H, "
-                        "SVR, pooling), max over ranks",
-               "pooled_vmaf_mean": res["pooled_metrics"]["vmaf"]["mean"]}
+               "frames": n_e2e, "steps": k_e2e, "calls": 1, "ms_per_step": 1000.0 * dt / k_e2e,
+               "timer": "host wall clock around one engine.analyze call over steps x frames_per_step pinned host frames (H2D, "
+                        "kernels, feature D2H per launch group, SVR, log entries, pooling), max over ranks",
+               "pooled_vmaf_mean": res["pooled_metrics"]["vmaf"]["mean"],
+               "one_call_per_step": {"value": fps_step * k_short * world / dt_s, "unit": "frames/s", "calls": k_short,
+                                     "frames_per_call": fps_step,
+                                     "pooled_vmaf_mean": res_s["pooled_metrics"]["vmaf"]["mean"]}}
         if cx.numa_note:
             e2e["host_placement"] = cx.numa_note
     return {"value": value, "ms_per_step": ms / steps, "steps": steps, "gpu_launches": int(launches), "clocks": clocks,

@@ -288,6 +288,20 @@ def shard_ranges(n_frames: int, n_shards: int, weights=None):
 
 _FIRST_KICK = 8
 _EARLY_MIN = 64            # rows worth building ahead of the drain (below that the tail is short anyway)
+_EARLY_STEP = 512          # long clips: build the log entries of finished frames every so many submitted frames
+
+
+def _hand_over(fx, rows, early, handed: int, done: int, lead: int) -> int:
+    """Rows of the ordinals [handed, done) -- complete on the GPU and read back already -- go into `rows`, and `early`
+    is told how far the clip is known now.  Returns the new `handed`.  The submitting thread does this between two
+    launch groups: it waits for a free ring slot most of the time anyway, and the GPU has up to three groups queued."""
+    if done - max(handed, lead) < _EARLY_MIN:
+        return handed
+    out = np.ctypeslib.as_array(fx.fetch(handed, done - handed))
+    skip = max(lead - handed, 0)
+    rows.put(out["frame_index"][skip:], out[skip:])
+    early(int(out["frame_index"][-1]) + 1)
+    return done
 
 
 class _Cancelled(Exception):
@@ -328,6 +342,9 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
                 [(pinned_planes(shapes, dtype), pinned_planes(shapes, dtype)) for _ in range(2 * B)]
         lead = (1 if start > 0 else 0) if lead_in is None else (1 if lead_in and start > 0 else 0)
         ordinal = 0
+        handed = 0                      # ordinals whose rows were already handed to `early`
+        if not isinstance(rows, Rows):
+            early = None
         ids = list(range(start - lead, end))
         if not zero_copy:
             # raw files: several readers (page-cache copies run beside each other); a decoder is one sequential stream
@@ -368,6 +385,8 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
                 flags |= L.FRAME_SKIP_SPATIAL
             fx.submit(i, rp, dp, flags)
             ordinal += 1
+            if early is not None and ordinal - handed >= _EARLY_STEP and ordinal % B == 0:
+                handed = _hand_over(fx, rows, early, handed, min(int(fx.frames_done()), ordinal), lead)
             left = end - 1 - i              # frames still to submit
             if (ordinal == min(_FIRST_KICK, B // 2) and B > 1) or (tail_split and left >= 2 and left in (B // 2, B // 4)):
                 # start the GPU on a short first group (the pipeline fills sooner) and split the tail into halving
@@ -376,27 +395,21 @@ def _run_shard(src: FrameSource, model: VmafModel, opt: EngineOptions, device: i
                 fx.kick()
             if progress:
                 progress(1)
-        got = 0
-        if early is not None and isinstance(rows, Rows) and ordinal:
+        if early is not None and ordinal:
             # Up to three launch groups are still on the GPU when the last frame has been submitted (a few ms of work).
             # Start the last (partial) group now and hand every row that is already complete to `early`, which builds
             # those frames' log entries while the GPU drains -- instead of doing all of it after the drain.
             fx.kick()
-            got = min(int(fx.frames_done()), ordinal)
-            if got - lead >= _EARLY_MIN:
-                out = np.ctypeslib.as_array(fx.fetch(0, got))
-                rows.put(out["frame_index"][lead:got], out[lead:got])
-                early(int(out["frame_index"][got - 1]) + 1)
-            else:
-                got = 0
+            handed = _hand_over(fx, rows, early, handed, min(int(fx.frames_done()), ordinal), lead)
         fx.flush()
-        out = np.ctypeslib.as_array(fx.fetch(got, ordinal - got))       # structured view of the bv_frame_features records
-        skip = max(lead - got, 0)
-        if isinstance(rows, Rows):
-            rows.put(out["frame_index"][skip:], out[skip:])
-        else:
-            for k in range(skip, len(out)):
-                rows[int(out["frame_index"][k])] = RowView(out, k)
+        if ordinal > handed:
+            out = np.ctypeslib.as_array(fx.fetch(handed, ordinal - handed))     # structured view of the bv_frame_features records
+            skip = max(lead - handed, 0)
+            if isinstance(rows, Rows):
+                rows.put(out["frame_index"][skip:], out[skip:])
+            else:
+                for k in range(skip, len(out)):
+                    rows[int(out["frame_index"][k])] = RowView(out, k)
     except _Cancelled:
         errors.append(("cancelled", None))
     except Exception as e:            # surfaced by analyze(): the caller decides how to report
@@ -799,18 +812,29 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
     holders: list = []
     t0 = time.perf_counter()
     threads = []
-    head: dict = {}
+    head = {"frames": [], "cols": [], "upto": first}
 
-    def build_early(hi):
-        """Runs on the shard thread while the GPU finishes its last launch groups: log entries of the frames [first, hi - 1)
-        from the rows that are complete already (frame hi - 1 waits for its successor's motion)."""
+    def build_block(hi, final):
+        """Log entries of the frames [head.upto, hi) from rows that are complete (frame hi - 1 waits for its successor's
+        motion unless the clip ends there).  Called on the shard thread while the GPU works on later frames (`build_early`)
+        and once more after the last row has arrived."""
+        s0 = head["upto"]
+        if hi - s0 < (1 if final else 2):
+            return
         cols: dict = {}
         with _NoGc():
-            frs = _build_frames_block(rows[first:hi], model, opt, devices[0], None, True, cols)
-        keep = sum(1 for fr in frs if fr["frameNum"] < hi - 1 - first)
-        if keep and cols:
-            head.update(frames=frs[:keep], upto=hi - 1,
-                        cols={nm: (v[:keep], None if ok is None else ok[:keep]) for nm, (v, ok) in cols.items()})
+            frs = _build_frames_block(rows[s0:hi], model, opt, devices[0], None, s0 == first, cols)
+        keep = len(frs) if final else sum(1 for fr in frs if fr["frameNum"] < hi - 1 - s0)
+        for fr in frs[:keep]:
+            fr["frameNum"] += s0
+        head["frames"] += frs[:keep]
+        if cols:
+            head["cols"].append({nm: (v[:keep], None if ok is None else ok[:keep]) for nm, (v, ok) in cols.items()})
+        head["upto"] = hi if final else hi - 1
+
+    def build_early(hi):
+        build_block(hi, False)
+
     # Long clips on several GPUs: the devices pull chunks of `dynamic_chunk` frames from a shared counter instead of
     # each getting one fixed share.  The GPUs of one box do not see the same host-to-device bandwidth under load (four
     # of the eight B200s share a host bridge: ~24 vs ~36 GB/s each, tools/h2d_concurrent.py), and with equal shares the
@@ -863,24 +887,13 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
         if n <= 0:
             raise EOFError("no frame could be decoded")
     rows_used = rows[first:last]
+    if head["upto"] > last:             # a truncated clip that ends before what was built ahead: start over
+        head.update(frames=[], cols=[], upto=first)
+    build_block(last, True)
+    frames = head["frames"]
     pooled_out: dict = {}
-    if head and head["upto"] < last:
-        # the rest of the clip, continuing where the early block stopped; pooling runs over both blocks' columns
-        s0 = head["upto"]
-        cols: dict = {}
-        with _NoGc():
-            tail = _build_frames_block(rows[s0:last], model, opt, devices[0], None, False, cols)
-        for fr in tail:
-            fr["frameNum"] += s0 - first
-        frames = head["frames"] + tail
-        if cols:
-            pooled_out["pooled"] = _pool_columns([head["cols"], cols])
-        elif not tail:
-            pooled_out["pooled"] = _pool_columns([head["cols"]])
-    else:
-        frames = build_frames(rows_used, model, opt, devices[0], pooled_out)
-    for fr in frames:
-        fr["frameNum"] += first
+    if head["cols"] and not model.bootstrap:
+        pooled_out["pooled"] = _pool_columns(head["cols"])
     dt = time.perf_counter() - t0
     pooled = pooled_out.get("pooled") or report.pooled_metrics(frames)
     return {"version": report.VERSION, "fps": n / dt if dt > 0 else 0.0, "frames": frames,

@@ -164,6 +164,28 @@ def test_tail_split_only_for_reduced_group_sizes(fake, monkeypatch):
     assert fx.kicks == [8, 92, 96, 100]
 
 
+def test_long_clips_are_built_in_steps_while_frames_are_still_submitted(fake, monkeypatch):
+    """Every 512 submitted frames the rows that are complete go to the frame builder (the submitting thread waits for ring
+    slots most of the time anyway); the seams between the blocks -- motion2 needs the next frame -- and the pooled report
+    must equal the one-pass build of the same rows."""
+    model = M.resolve_model("vmaf_v0.6.1")
+    calls = []
+    real = engine._build_frames_block
+    monkeypatch.setattr(engine, "_build_frames_block", lambda *a, **k: (calls.append(len(a[0])), real(*a, **k))[1])
+    n = 1700
+    one = engine.analyze(Clip(n), model, _opt(psnr=True, n_subsample=2, devices=(0,)))
+    # a hand-over once 512 more frames than at the last one are submitted (at a group boundary): 512, 992 and 1472 submitted
+    # -> 472, 952, 1432 complete (40 "in flight"); then the one before the drain (1660 complete) and the rest.  Each block
+    # starts one frame early: the last frame of a block waits for its successor's motion
+    assert calls == [472, 952 - 471, 1432 - 951, 1660 - 1431, 1700 - 1659]
+    fake.instances.clear()
+    calls.clear()
+    two = engine.analyze(Clip(n), model, _opt(psnr=True, n_subsample=2, devices=(0, 0)))
+    assert calls == [n]
+    assert one["frames"] == two["frames"] and one["pooled_metrics"] == two["pooled_metrics"]
+    assert [fr["frameNum"] for fr in one["frames"]] == list(range(0, n, 2))
+
+
 @pytest.mark.parametrize("n,sub,rng", [(200, 1, None), (131, 3, None), (300, 1, (17, 260)), (105, 1, None), (90, 1, None)])
 def test_frames_built_during_the_drain_equal_the_one_pass_build(fake, monkeypatch, n, sub, rng):
     """A single-shard analysis hands the rows that are complete when the last frame has been submitted to the frame

@@ -9,7 +9,8 @@ wname = sys.argv[1] if len(sys.argv) > 1 else "1080p-float"
 wl = bench.WORKLOADS[wname]
 pool = bench.Pool(wl["w"], wl["h"], wl["bpc"], wl["pool"], 100, False, 0, resident=False)
 model = M.resolve_model(wl["model"])
-opt = engine.EngineOptions(devices=(0,), psnr=wl["psnr"], ssim=wl["ssim"], ms_ssim=wl["ms_ssim"])
+ndev = int(sys.argv[2]) if len(sys.argv) > 2 else 1          # contexts on GPU 0 (frame shards run beside each other)
+opt = engine.EngineOptions(devices=(0,) * ndev, psnr=wl["psnr"], ssim=wl["ssim"], ms_ssim=wl["ms_ssim"])
 T = {}
 def wrap(cls, name):
     f = getattr(cls, name)
@@ -30,5 +31,5 @@ with engine.Engine() as sess:
         res = sess.analyze(pool.clip(n), model, opt)
         dt = time.perf_counter() - t0
         rest = dt - sum(T.values())
-        print(f"{wname} call {rep}: {1e3 * dt:7.2f} ms = {n / dt:7.1f} fps | " +
+        print(f"{wname} x{ndev} call {rep}: {1e3 * dt:7.2f} ms = {n / dt:7.1f} fps | " +
               " ".join(f"{k} {1e3 * v:.2f}" for k, v in T.items()) + f" | other {1e3 * rest:.2f}")
