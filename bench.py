@@ -42,6 +42,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+CONTEXTS_PER_GPU = 3        # what engine.analyze picks for clips of >= 1536 frames per GPU (EngineOptions.contexts_per_device)
 WORKLOADS = {
     "1080p-float": dict(w=1920, h=1080, bpc=8, model="vmaf_float_v0.6.1", psnr=True, ssim=True, ms_ssim=True,
                         frames_per_step=512, pool=64, cfg="configs[1]"),
@@ -304,7 +305,9 @@ def bench_config(wl, wname, fps, n_gpus) -> dict:
             "planes": "Y, Cb, Cr (psnr=1 reads all three)" if chroma else "Y (every enabled feature reads luma only)",
             "l2_policy": "inputs larger than L2: each step streams the whole resident pool "
                          f"({wl['pool']} frame pairs, {mb:.0f} MB) through the kernels",
-            "parallelism": f"frame-sharded x{n_gpus}, no collective"}
+            "contexts_per_gpu": CONTEXTS_PER_GPU,
+            "parallelism": f"frame-sharded x{n_gpus}, no collective; {CONTEXTS_PER_GPU} contexts side by side on each GPU, a "
+                           "contiguous share of the frames each (the engine's choice for a clip of this length)"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -436,27 +439,52 @@ def measure_workload(cx: Ctx, wname: str, wl: dict, pool: Pool, steps: int, warm
             fx.submit_device(i, pool.dev_planes(i, 0), pool.dev_planes(i, 1), L.FRAME_FIRST if i == 0 else 0)
             counter[0] += 1
 
-    # ---- resident run: W warm-up steps, then exactly K timed steps
-    for _ in range(max(warmup, 3)):
-        run_step()
-    fx.flush()
+    # ---- resident run: W warm-up steps, then exactly K timed steps.  As the engine does for a clip of this length
+    # (EngineOptions.contexts_per_device), the steps' frames are dealt over CONTEXTS_PER_GPU contexts that run side by side
+    # on this GPU, each a contiguous share submitted by its own host thread; the stopwatch is a pair of CUDA events on the
+    # first context's compute stream: the first before anything is submitted, the second after every context has drained.
+    others = [FeatureExtractor(w, h, bpc, 420 if pool.chroma else 0, mask, local, vif_enhn_gain_limit=model.vif_enhn_gain_limit,
+                               adm_enhn_gain_limit=model.adm_enhn_gain_limit, fast_float=fast)
+              for _ in range(CONTEXTS_PER_GPU - 1)]
+    ctxs = [fx] + others
+
+    def run_share(fxk, first, count):
+        for i in range(first, first + count):
+            fxk.submit_device(i, pool.dev_planes(i, 0), pool.dev_planes(i, 1), L.FRAME_FIRST if i == first else 0)
+        fxk.kick()                          # the share's last (partial) launch group
+
+    def run_all(total):
+        share = (total + len(ctxs) - 1) // len(ctxs)
+        ths = [threading.Thread(target=run_share, args=(c, k * share, max(0, min(share, total - k * share))))
+               for k, c in enumerate(ctxs)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        for c in ctxs:
+            c.flush()
+
+    run_all(fps_step * max(warmup, 3))
+    for c in ctxs:
+        c.reset()
     sampler = ClockSampler(local) if with_clocks else None
     cx.barrier()
-    fx.flush()
-    launches0 = fx.kernel_launches
+    launches0 = sum(c.kernel_launches for c in ctxs)
     if sampler:
         sampler.start()
     fx.timer_mark(0)
-    for _ in range(steps):
-        run_step()
+    run_all(fps_step * steps)
     fx.timer_mark(1)
     fx.flush()
     ms = fx.timer_elapsed_ms()
     cx.barrier()
     clocks = sampler.stop() if sampler else None
-    launches = fx.kernel_launches - launches0
+    launches = sum(c.kernel_launches for c in ctxs) - launches0
     ms = cx.max_over_ranks(ms)
     value = fps_step * steps * world / (ms / 1000.0)
+    for c in others:
+        c.close()
+    fx.reset()
 
     # ---- per-kernel profile over the same region (events around every launch; a separate pass so the
     #      event overhead stays out of `value`)

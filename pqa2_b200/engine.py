@@ -44,7 +44,7 @@ class EngineOptions:
     fast_float: bool = False         # float models only, opt-in: contracted / folded-tap stencils (bv_opts.fast_float)
     dynamic_chunk: int = 512         # frames per chunk when several contexts share a long clip (>= 4 chunks each); 0 = fixed shares
     contexts_per_device: int = 0     # contexts (frame shards side by side) on EACH GPU of `devices`; 0 = auto: 3 for a clip
-                                     # long enough to be dealt in chunks, else 1.  One context runs its ~25 kernels per
+                                     # long enough to be dealt in chunks (>= 1536 frames per GPU), else 1.  One context runs its ~25 kernels per
                                      # launch group back to back on one stream, and the small pyramid levels, the
                                      # reductions and every kernel's last wave leave SMs idle; a second and third
                                      # context's kernels fill them: +6-8 % frames/s on one B200, same bits
@@ -294,6 +294,7 @@ def shard_ranges(n_frames: int, n_shards: int, weights=None):
 _FIRST_KICK = 8
 _EARLY_MIN = 64            # rows worth building ahead of the drain (below that the tail is short anyway)
 _EARLY_STEP = 512          # long clips: build the log entries of finished frames every so many submitted frames
+_MIN_CHUNK = 128           # shortest chunk worth a lead-in frame and a pipeline fill of its own (four launch groups)
 
 
 def _hand_over(fx, rows, early, handed: int, done: int, lead: int) -> int:
@@ -806,9 +807,11 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
     sequential = bool(getattr(src, "sequential", False))
     per_dev = opt.contexts_per_device
     if per_dev <= 0:
-        per_dev = 3 if (chunk > 0 and not sequential and n >= 4 * 3 * len(devices) * chunk) else 1
+        per_dev = 3 if (chunk > 0 and not sequential and n >= 4 * 3 * len(devices) * _MIN_CHUNK) else 1
     if per_dev > 1 and not sequential:
         devices = [d for d in devices for _ in range(per_dev)]          # contexts of one GPU take neighbouring chunks
+        if chunk > 0:                   # at least four chunks per context, so that their fills and drains interleave
+            chunk = min(chunk, max(_MIN_CHUNK, n // (4 * len(devices))))
     ranges = [(first + a, first + b) for a, b in shard_ranges(n, len(devices))]
     done = [0]
     lock = threading.Lock()

@@ -173,17 +173,29 @@ def test_long_clips_are_built_in_steps_while_frames_are_still_submitted(fake, mo
     real = engine._build_frames_block
     monkeypatch.setattr(engine, "_build_frames_block", lambda *a, **k: (calls.append(len(a[0])), real(*a, **k))[1])
     n = 1700
-    one = engine.analyze(Clip(n), model, _opt(psnr=True, n_subsample=2, devices=(0,)))
+    one = engine.analyze(Clip(n), model, _opt(psnr=True, n_subsample=2, devices=(0,), contexts_per_device=1))
     # a hand-over once 512 more frames than at the last one are submitted (at a group boundary): 512, 992 and 1472 submitted
     # -> 472, 952, 1432 complete (40 "in flight"); then the one before the drain (1660 complete) and the rest.  Each block
     # starts one frame early: the last frame of a block waits for its successor's motion
     assert calls == [472, 952 - 471, 1432 - 951, 1660 - 1431, 1700 - 1659]
     fake.instances.clear()
     calls.clear()
-    two = engine.analyze(Clip(n), model, _opt(psnr=True, n_subsample=2, devices=(0, 0)))
+    two = engine.analyze(Clip(n), model, _opt(psnr=True, n_subsample=2, devices=(0, 0), contexts_per_device=1,
+                                              dynamic_chunk=0))
     assert calls == [n]
     assert one["frames"] == two["frames"] and one["pooled_metrics"] == two["pooled_metrics"]
     assert [fr["frameNum"] for fr in one["frames"]] == list(range(0, n, 2))
+    # the default for a clip of this length: three contexts side by side on the GPU, chunks of n // 12 frames from a shared
+    # counter, the waiting thread building the finished prefix -- same log
+    fake.instances.clear()
+    calls.clear()
+    auto = engine.analyze(Clip(n), model, _opt(psnr=True, n_subsample=2, devices=(0,)))
+    assert len(fake.instances) == 3 and sum(calls) >= n and len(calls) >= 1
+    starts = sorted({fx.frames[0][0] for fx in fake.instances})
+    assert auto["frames"] == one["frames"] and auto["pooled_metrics"] == one["pooled_metrics"]
+    short = engine.analyze(Clip(1000), model, _opt(devices=(0,)))
+    assert len(fake.instances) == 4                                       # below 1536 frames: one context
+    assert len(short["frames"]) == 1000
 
 
 @pytest.mark.parametrize("n,sub,rng", [(200, 1, None), (131, 3, None), (300, 1, (17, 260)), (105, 1, None), (90, 1, None)])
