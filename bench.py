@@ -551,8 +551,10 @@ def measure_workload(cx: Ctx, wname: str, wl: dict, pool: Pool, steps: int, warm
         # complete, and SVR fusion + log entries + pooling of the whole clip before the call returns.
         k_e2e = max(1, steps)
         with engine.Engine() as sess:
-            for _ in range(2):
-                sess.analyze(pool.clip(fps_step), model, opt)                    # warm-up (allocations, first launches)
+            # warm-up (allocations, first launches): a short clip (one context) and one long enough for the engine to
+            # bring up the contexts it runs side by side on a long clip (EngineOptions.contexts_per_device)
+            sess.analyze(pool.clip(fps_step), model, opt)
+            sess.analyze(pool.clip(min(fps_step * k_e2e, max(fps_step, 2048))), model, opt)
             cx.barrier()
             t0 = time.perf_counter()
             res = sess.analyze(pool.clip(fps_step * k_e2e), model, opt)
