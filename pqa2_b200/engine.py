@@ -813,6 +813,9 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
         if chunk > 0:                   # at least four chunks per context, so that their fills and drains interleave
             chunk = min(chunk, max(_MIN_CHUNK, n // (4 * len(devices))))
     ranges = [(first + a, first + b) for a, b in shard_ranges(n, len(devices))]
+    if len(devices) != len(opt.devices):
+        from dataclasses import replace
+        opt = replace(opt, devices=tuple(devices))          # the shards share the host's reader threads by this count
     done = [0]
     lock = threading.Lock()
 
