@@ -684,14 +684,14 @@ def measure_batch(cx: Ctx, pool: Pool) -> dict:
     opt = engine.EngineOptions(devices=(cx.local,))
     nclips, nfr = cx.args.batch_clips, BATCH_FRAMES
     clips = [pool.clip(nfr, offset=5 * k, stride=1 + k % 3) for k in range(nclips)]
-    with engine.Engine() as sess, engine.Engine() as sess2:
-        # warm-up: the contexts and first launches of both workers' sessions, and the process group's first object gather (a
+    with engine.Engine() as sess, engine.Engine() as sess2, engine.Engine() as sess3:
+        # warm-up: the contexts and first launches of the workers' sessions, and the process group's first object gather (a
         # fresh NCCL communicator sets up its channels lazily -- about a second at 8 ranks -- which is not the sweep's cost)
-        D.analyze_batch_distributed([pool.clip(64) for _ in range(2 * cx.world)], model, opt, device=cx.local,
-                                    session=[sess, sess2])
+        D.analyze_batch_distributed([pool.clip(64) for _ in range(3 * cx.world)], model, opt, device=cx.local,
+                                    session=[sess, sess2, sess3])
         cx.barrier()
         t0 = time.perf_counter()
-        out = D.analyze_batch_distributed(clips, model, opt, device=cx.local, session=[sess, sess2])
+        out = D.analyze_batch_distributed(clips, model, opt, device=cx.local, session=[sess, sess2, sess3])
         dt = cx.max_over_ranks(time.perf_counter() - t0)
     if cx.rank != 0:
         return None
@@ -700,7 +700,7 @@ def measure_batch(cx: Ctx, pool: Pool) -> dict:
     return {"value": (nclips * nfr / dt) if not errs else None, "unit": "frames/s", "clips": nclips, "frames_per_clip": nfr,
             "clips_per_s": nclips / dt, "seconds": dt, "n_gpus": cx.world, "scaling": "strong", "failed_clips": len(errs),
             "workload": f"configs[4]: {nclips} clips x {nfr} frames 1920x1080 8-bit (pinned pool of {pool.P} frame pairs, a "
-                        "different walk per clip), vmaf_v0.6.1, clip k on rank k % N, two clips in flight per rank (a session each)",
+                        "different walk per clip), vmaf_v0.6.1, clip k on rank k % N, three clips in flight per rank (a session each)",
             "pooled_reports": len(means), "sum_of_pooled_vmaf_means": float(np.sum(np.array(means))) if means else None,
             "h2d_bytes_total": int(2 * pool.plane_bytes[0] * nclips * nfr),
             "timer": "host wall clock around dist.analyze_batch_distributed, max over ranks"}

@@ -935,12 +935,12 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
 
 
 def analyze_batch(clips: list, model: VmafModel, opt: EngineOptions | None = None, devices=None,
-                  progress_cb=None, concurrency: int = 2) -> list:
+                  progress_cb=None, concurrency: int = 3) -> list:
     """Many clips over many GPUs (BASELINE.json configs[4]: a sweep of 64 1080p clip pairs on 8 B200).
 
     Whole clips are the unit here -- no lead-in frames, no cross-GPU state: every GPU has ``concurrency`` workers, each
     with its own session (one context, reused for every clip of the same geometry), which take the next clip from a
-    shared list; two clips in flight per GPU fill the few ms a single clip leaves idle while its pipeline fills and while
+    shared list; three clips in flight per GPU fill the few ms a single clip leaves idle while its pipeline fills and while
     its last launch groups drain and are scored.  Returns one libvmaf log dict per clip, in input order; a clip that
     fails yields ``{"error": str}`` in its slot (the reference's per-clip error convention)."""
     opt = opt or EngineOptions()

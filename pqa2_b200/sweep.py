@@ -5,7 +5,7 @@ The reference runs one ffmpeg child per pair, one after another, and the GUI the
 ``<test>_<stamp>_vmaf.json`` (``app/vmaf_analyzer.py:304``), ``<test>_<stamp>_metadata.json``
 (``app/ui/tabs/analysis_tab.py:765-811``) and on request the per-test / combined CSV exports
 (``app/ui/tabs/results_tab.py:3518-3696``).  Here whole clips are dealt round-robin to the devices
-(``engine.analyze_batch``: two clips in flight per GPU, a session each, no lead-in frames, no collective) and the same files are written
+(``engine.analyze_batch``: three clips in flight per GPU, a session each, no lead-in frames, no collective) and the same files are written
 from the returned logs."""
 from __future__ import annotations
 
