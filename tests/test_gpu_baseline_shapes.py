@@ -161,3 +161,26 @@ def test_dynamic_chunks_match_one_shard():
         dyn = engine.analyze(src, model, engine.EngineOptions(devices=(0, 0), dynamic_chunk=24))
         assert [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in dyn["frames"]]
         assert np.array_equal(one["rows"].arr["raw"], dyn["rows"].arr["raw"])
+
+
+def test_three_contexts_per_gpu_match_one_context():
+    """What engine.analyze does by default for a clip of >= 1536 frames: three contexts side by side on the GPU, chunks
+    from a shared counter, log entries built while frames are in flight -- against one context and a one-pass build: every
+    frame's metrics, the raw accumulators and the pooled report, integer and float model."""
+    w, h, n = 192, 108, 1600
+
+    class Cycled(engine.SynthSource):                       # 40 distinct frames, cycled (synthesis would dominate the test)
+        def read_into(self, i, ref_planes, dis_planes, luma_only):
+            super().read_into(i % 40, ref_planes, dis_planes, luma_only)
+
+    src = Cycled(w, h, 8, n, seed=31, chroma=0)
+    for name in ("vmaf_v0.6.1", "vmaf_float_v0.6.1"):
+        model = M.resolve_model(name)
+        with engine.Engine() as sess:
+            one = sess.analyze(src, model, engine.EngineOptions(devices=(0,), contexts_per_device=1, psnr=True))
+            auto = sess.analyze(src, model, engine.EngineOptions(devices=(0,), psnr=True))
+            assert len({k[1] for k in sess._fx}) == 3         # three shard contexts were brought up for the second call
+        assert [fr["frameNum"] for fr in auto["frames"]] == list(range(n))
+        assert [fr["metrics"] for fr in one["frames"]] == [fr["metrics"] for fr in auto["frames"]]
+        assert np.array_equal(one["rows"].arr["raw"], auto["rows"].arr["raw"])
+        assert one["pooled_metrics"] == auto["pooled_metrics"]
