@@ -294,7 +294,8 @@ def wl_dtype(wl) -> str:
     return "f32" if "float" in wl["model"] else "int32/int64 fixed-point"
 
 
-def bench_config(wl, wname, fps, n_gpus) -> dict:
+def bench_config(wl, wname, fps, n_gpus, contexts=None) -> dict:
+    contexts = CONTEXTS_PER_GPU if contexts is None else max(1, contexts)
     chroma = False          # libvmaf psnr=1 is psnr_y (enable_chroma=false through FFmpeg): every enabled feature reads luma
     bps = 1 if wl["bpc"] == 8 else 2
     mb = wl["pool"] * 2 * wl["w"] * wl["h"] * bps * (1.5 if chroma else 1.0) / 1e6
@@ -305,8 +306,8 @@ def bench_config(wl, wname, fps, n_gpus) -> dict:
             "planes": "Y, Cb, Cr (psnr=1 reads all three)" if chroma else "Y (every enabled feature reads luma only)",
             "l2_policy": "inputs larger than L2: each step streams the whole resident pool "
                          f"({wl['pool']} frame pairs, {mb:.0f} MB) through the kernels",
-            "contexts_per_gpu": CONTEXTS_PER_GPU,
-            "parallelism": f"frame-sharded x{n_gpus}, no collective; {CONTEXTS_PER_GPU} contexts side by side on each GPU, a "
+            "contexts_per_gpu": contexts,
+            "parallelism": f"frame-sharded x{n_gpus}, no collective; {contexts} context(s) side by side on each GPU, a "
                            "contiguous share of the frames each (the engine's choice for a clip of this length)"}
 
 
@@ -445,7 +446,7 @@ def measure_workload(cx: Ctx, wname: str, wl: dict, pool: Pool, steps: int, warm
     # first context's compute stream: the first before anything is submitted, the second after every context has drained.
     others = [FeatureExtractor(w, h, bpc, 420 if pool.chroma else 0, mask, local, vif_enhn_gain_limit=model.vif_enhn_gain_limit,
                                adm_enhn_gain_limit=model.adm_enhn_gain_limit, fast_float=fast)
-              for _ in range(CONTEXTS_PER_GPU - 1)]
+              for _ in range(max(1, args.contexts) - 1)]
     ctxs = [fx] + others
 
     def run_share(fxk, first, count):
@@ -795,6 +796,8 @@ def main() -> int:
     ap.add_argument("--fast-float", action="store_true", help="float workloads with bv_opts.fast_float (opt-in build)")
     ap.add_argument("--sharded-frames", type=int, default=SHARDED_FRAMES)
     ap.add_argument("--batch-clips", type=int, default=BATCH_CLIPS)
+    ap.add_argument("--contexts", type=int, default=CONTEXTS_PER_GPU,
+                    help="contexts side by side on each GPU in the resident run (1: one stream of launches, for ncu captures)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -904,14 +907,14 @@ def main() -> int:
                 rec["cpu_baseline"] = cb(WORKLOADS[nm])
     for nm, rec in workloads.items():
         if "roofline" in rec:
-            rec["config"] = bench_config(WORKLOADS[nm], nm, args.frames_per_step or WORKLOADS[nm]["frames_per_step"], world)
+            rec["config"] = bench_config(WORKLOADS[nm], nm, args.frames_per_step or WORKLOADS[nm]["frames_per_step"], world, args.contexts)
             rec["dtype"] = wl_dtype(WORKLOADS[nm])
             rec["unit"] = "frames/s"
 
     out = {"metric": "vmaf_frames_per_sec", "value": head["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": wl_dtype(wl), "data": "synthetic",
-           "config": bench_config(wl, wname, fps_step, world), "clocks": head["clocks"], "e2e": head["e2e"],
+           "config": bench_config(wl, wname, fps_step, world, args.contexts), "clocks": head["clocks"], "e2e": head["e2e"],
            "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": base,
            "kernels": head["kernels"],
            "published_reference_fps": "23-26 fps (1080p, libvmaf n_threads=4, decode included; BASELINE.md §1)"}

@@ -5,7 +5,7 @@ TAG=${1:-v1}
 O=gpurun_out
 python bench.py --steps 20 --warmup 3 > $O/r02_bench_$TAG.json 2> $O/r02_bench_$TAG.err || exit 1
 python bench.py --impl reference --steps 2 --warmup 1 > $O/r02_bench_reference_$TAG.json 2>> $O/r02_bench_$TAG.err
-X="--steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras"
+X="--steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras --contexts 1"     # one context: the launches of a frame group stay in order
 # numbers printed under ncu are never bench values
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/r02_launches_$TAG.csv \
     python bench.py $X > $O/ncu_launches_$TAG.log 2>&1
