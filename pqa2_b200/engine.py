@@ -886,13 +886,17 @@ def analyze(src: FrameSource, model: VmafModel, opt: EngineOptions | None = None
             threads.append(th)
         # this thread has nothing to do but wait: it builds the log entries of the clip's finished prefix meanwhile
         prefix = first
-        while any(th.is_alive() for th in threads) and not model.bootstrap:
-            with arrived:
-                arrived.wait(0.02)
-                while prefix in finished:
-                    prefix = finished.pop(prefix)
-            if prefix - head["upto"] >= _EARLY_STEP and not errors:
-                build_block(prefix, False)
+        try:
+            while any(th.is_alive() for th in threads) and not model.bootstrap:
+                with arrived:
+                    arrived.wait(0.02)
+                    while prefix in finished:
+                        prefix = finished.pop(prefix)
+                if prefix - head["upto"] >= _EARLY_STEP and not errors:
+                    build_block(prefix, False)
+        except Exception as e:            # noqa: BLE001  (e.g. the SVR call failed): stop the workers, then report it
+            errors.append(("error", e))
+            cancel.set()
     else:
         live = [(k, dev, a, b) for k, (dev, (a, b)) in enumerate(zip(devices, ranges)) if b > a]
         for k, dev, a, b in live:
