@@ -181,7 +181,10 @@ bv_model *bv_model_create(int n_feat, int n_sv, const double *sv, const double *
 void bv_model_free(bv_model *);
 /* feat: [n][n_feat] in the model's feature order; out: [n] final scores. */
 int  bv_predict(const bv_model *, const double *feat, int64_t n, unsigned flags, double *out);
-/* same, evaluated by the svr_predict CUDA kernel on `device` (one thread per (frame, SV) pair). */
+/* same, evaluated by the svr_predict CUDA kernel on `device` (one thread per (frame, SV) pair).  The model keeps, per
+ * device, a mirror of its vectors plus a stream and grow-only scratch of its own (freed by bv_model_free): a call neither
+ * allocates nor frees device memory, so it never waits for extractor kernels still running on that device.  Calls on one
+ * model are serialised; any thread may call. */
 int  bv_predict_device(const bv_model *, int device, const double *feat, int64_t n, unsigned flags, double *out);
 
 #ifdef __cplusplus
