@@ -51,20 +51,47 @@ static const int vif_fw[4] = { 17, 9, 5, 3 };
 
 ORC_API const float *orc_f_vif_filter(int scale) { return vif_ftab[scale]; }
 
-/* vif_tools.c vif_filter1d_s(): vertical then horizontal, mirrored borders, full-size output */
-static void vif_filter1d(const float *f, int fw, const float *src, float *dst, float *tmp, int w, int h)
+/* vif_tools.c vif_filter1d_s(): vertical then horizontal, mirrored borders, full-size output.  A row at a time, tap loop
+ * outside and column loop inside, so that gcc vectorises ACROSS pixels: every pixel still sees acc = 0, then
+ * acc += f[k] * v[k] for k = 0 .. fw-1 with each product and each sum rounded to float -- the scalar C order, bit for
+ * bit (-ffp-contract=off).  The two inner loops are built for AVX2 and for the baseline ISA; the loader picks. */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define ORC_SIMD __attribute__((target_clones("avx2", "default")))
+#else
+#define ORC_SIMD
+#endif
+
+ORC_SIMD void orc_f_fir_rows(const float *const *rows, const float *f, int fw, int w, float *restrict out)
 {
+    for (int j = 0; j < w; ++j) out[j] = 0.0f;
+    for (int k = 0; k < fw; ++k) {
+        const float *restrict v = rows[k];
+        const float fk = f[k];
+        for (int j = 0; j < w; ++j) out[j] += fk * v[j];
+    }
+}
+
+ORC_SIMD void orc_f_fir_shift(const float *restrict padded, const float *f, int fw, int w, float *restrict out)
+{
+    for (int j = 0; j < w; ++j) out[j] = 0.0f;
+    for (int k = 0; k < fw; ++k) {
+        const float fk = f[k];
+        for (int j = 0; j < w; ++j) out[j] += fk * padded[j + k];
+    }
+}
+
+static void vif_filter1d(const float *f, int fw, const float *src, float *dst, float *tmp /* w + fw */, int w, int h)
+{
+    const int r = fw / 2;
     for (int i = 0; i < h; ++i) {
-        for (int j = 0; j < w; ++j) {
-            float acc = 0;
-            for (int k = 0; k < fw; ++k) acc += f[k] * src[(size_t)mirror(i - fw / 2 + k, h) * w + j];
-            tmp[j] = acc;
+        const float *rows[17];
+        for (int k = 0; k < fw; ++k) rows[k] = src + (size_t)mirror(i - r + k, h) * w;
+        orc_f_fir_rows(rows, f, fw, w, tmp + r);
+        for (int m = 1; m <= r; ++m) {                  /* mirror(): -m -> m ; w - 1 + m -> w - m */
+            tmp[r - m] = tmp[r + m];
+            tmp[r + w - 1 + m] = tmp[r + w - m];
         }
-        for (int j = 0; j < w; ++j) {
-            float acc = 0;
-            for (int k = 0; k < fw; ++k) acc += f[k] * tmp[mirror(j - fw / 2 + k, w)];
-            dst[(size_t)i * w + j] = acc;
-        }
+        orc_f_fir_shift(tmp, f, fw, w, dst + (size_t)i * w);
     }
 }
 
@@ -120,7 +147,7 @@ ORC_API int orc_f_vif(const float *ref, const float *dis, int w, int h, double e
 {
     size_t n = (size_t)w * h;
     float *cr = malloc(4 * n), *cd = malloc(4 * n), *mu1 = malloc(4 * n), *mu2 = malloc(4 * n);
-    float *a = malloc(4 * n), *b = malloc(4 * n), *c = malloc(4 * n), *t = malloc(4 * n), *tmp = malloc(4 * (size_t)w);
+    float *a = malloc(4 * n), *b = malloc(4 * n), *c = malloc(4 * n), *t = malloc(4 * n), *tmp = malloc(4 * ((size_t)w + 17));
     memcpy(cr, ref, 4 * n); memcpy(cd, dis, 4 * n);
     for (int s = 0; s < 4; ++s) {
         const float *f = vif_ftab[s];

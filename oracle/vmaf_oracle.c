@@ -154,6 +154,60 @@ static inline uint16_t best16_from64(uint64_t v, int *x)
  *  0 num_log  1 den_log  2 num_non_log  3 den_non_log  4 accum_x  5 accum_x2  6 num_accum_x */
 enum { V_NUM_LOG, V_DEN_LOG, V_NUM_NONLOG, V_DEN_NONLOG, V_X, V_X2, V_CNT };
 
+/* The two filter passes run a whole row at a time -- tap loop outside, column loop inside, accumulators in row buffers --
+ * so that gcc vectorises them (integer sums: the order of the taps cannot change a bit); each hot loop is compiled for
+ * AVX2 and for the baseline ISA, the loader picks one (target_clones).  Same arithmetic as the per-pixel form of
+ * libvmaf's integer_vif.c, ~4x the frames/s: this file is also the CPU baseline bench.py reports. */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define ORC_SIMD __attribute__((target_clones("avx2", "default")))
+#else
+#define ORC_SIMD
+#endif
+
+/* a[j] += f * row[j] for the two pictures, and the three second-moment products */
+#define ORC_VPASS(T)                                                                            \
+    for (int k = 0; k < fw; ++k) {                                                              \
+        const T *xr = (const T *)rows_r[k], *yr = (const T *)rows_d[k];                         \
+        const uint32_t fk = f[k];                                                               \
+        for (int j = 0; j < w; ++j) {                                                           \
+            const uint32_t x = xr[j], y = yr[j];                                                \
+            const uint32_t fx = fk * x, fy = fk * y;                                            \
+            a_mu1[j] += fx; a_mu2[j] += fy;                                                     \
+            a_xx[j] += (uint64_t)fx * x; a_yy[j] += (uint64_t)fy * y; a_xy[j] += (uint64_t)fx * y; \
+        }                                                                                       \
+    }
+
+ORC_SIMD void orc_vif_vpass(const void *const *rows_r, const void *const *rows_d, int bytes_per_sample, int w, int fw,
+                            const uint16_t *f, uint32_t *a_mu1, uint32_t *a_mu2, uint64_t *a_xx, uint64_t *a_yy,
+                            uint64_t *a_xy)
+{
+    memset(a_mu1, 0, sizeof(uint32_t) * w); memset(a_mu2, 0, sizeof(uint32_t) * w);
+    memset(a_xx, 0, sizeof(uint64_t) * w); memset(a_yy, 0, sizeof(uint64_t) * w); memset(a_xy, 0, sizeof(uint64_t) * w);
+    if (bytes_per_sample == 1) { ORC_VPASS(uint8_t) } else { ORC_VPASS(uint16_t) }
+}
+
+/* horizontal pass over rows that carry their reflect-101 border (r samples on either side): no index arithmetic */
+ORC_SIMD void orc_vif_hpass(const uint16_t *p_mu1, const uint16_t *p_mu2, const uint32_t *p_xx, const uint32_t *p_yy,
+                            const uint32_t *p_xy, int w, int fw, const uint16_t *f, uint32_t *h_mu1, uint32_t *h_mu2,
+                            uint64_t *h_xx, uint64_t *h_yy, uint64_t *h_xy)
+{
+    memset(h_mu1, 0, sizeof(uint32_t) * w); memset(h_mu2, 0, sizeof(uint32_t) * w);
+    memset(h_xx, 0, sizeof(uint64_t) * w); memset(h_yy, 0, sizeof(uint64_t) * w); memset(h_xy, 0, sizeof(uint64_t) * w);
+    for (int k = 0; k < fw; ++k) {
+        const uint32_t fk = f[k];
+        for (int j = 0; j < w; ++j) {
+            h_mu1[j] += fk * (uint32_t)p_mu1[j + k];
+            h_mu2[j] += fk * (uint32_t)p_mu2[j + k];
+            h_xx[j] += (uint64_t)fk * p_xx[j + k];
+            h_yy[j] += (uint64_t)fk * p_yy[j + k];
+            h_xy[j] += (uint64_t)fk * p_xy[j + k];
+        }
+    }
+}
+
+#define ORC_REFLECT_BORDER(p, w, r)                                                             \
+    for (int m = 1; m <= (r); ++m) { (p)[(r) - m] = (p)[(r) + m]; (p)[(r) + (w) - 1 + m] = (p)[(r) + (w) - 1 - m]; }
+
 /* One scale of the statistic.  img is either the source picture (scale 0, bpc samples) or a
  * u16 pyramid level (scale > 0; passed with bpc = 16 semantics: shift 16).                 */
 static void vif_statistic(const void *ref, const void *dis, int src_bpc, ptrdiff_t stride,
@@ -171,48 +225,45 @@ static void vif_statistic(const void *ref, const void *dis, int src_bpc, ptrdiff
         sh_v = 16; rnd_v = 32768; sh_v_sq = 16; rnd_v_sq = 32768;
     }
     const int32_t sigma_nsq = 65536 << 1;
+    const int bps = src_bpc == 8 ? 1 : 2;
+    const size_t pw = (size_t)w + 2 * r;                 /* padded row: r border samples on either side */
 
-    uint16_t *t_mu1 = malloc(sizeof(uint16_t) * w), *t_mu2 = malloc(sizeof(uint16_t) * w);
-    uint32_t *t_xx = malloc(sizeof(uint32_t) * w), *t_yy = malloc(sizeof(uint32_t) * w),
-             *t_xy = malloc(sizeof(uint32_t) * w);
+    uint16_t *t_mu1 = malloc(sizeof(uint16_t) * pw), *t_mu2 = malloc(sizeof(uint16_t) * pw);
+    uint32_t *t_xx = malloc(sizeof(uint32_t) * pw), *t_yy = malloc(sizeof(uint32_t) * pw),
+             *t_xy = malloc(sizeof(uint32_t) * pw);
+    uint32_t *a_mu1 = malloc(sizeof(uint32_t) * w), *a_mu2 = malloc(sizeof(uint32_t) * w);
+    uint64_t *a_xx = malloc(sizeof(uint64_t) * w), *a_yy = malloc(sizeof(uint64_t) * w),
+             *a_xy = malloc(sizeof(uint64_t) * w);
     memset(acc, 0, sizeof(int64_t) * 7);
 
     for (int i = 0; i < h; ++i) {
         /* vertical pass over the (reflect-101 padded) column */
-        for (int j = 0; j < w; ++j) {
-            uint32_t a_mu1 = 0, a_mu2 = 0;
-            uint64_t a_xx = 0, a_yy = 0, a_xy = 0;
-            for (int k = 0; k < fw; ++k) {
-                int ii = reflect101(i - r + k, h);
-                uint32_t x = px(ref, src_bpc, stride, ii, j), y = px(dis, src_bpc, stride, ii, j);
-                uint32_t fx = f[k] * x, fy = f[k] * y;
-                a_mu1 += fx; a_mu2 += fy;
-                a_xx += (uint64_t)fx * x; a_yy += (uint64_t)fy * y; a_xy += (uint64_t)fx * y;
-            }
-            t_mu1[j] = (uint16_t)((a_mu1 + rnd_v) >> sh_v);
-            t_mu2[j] = (uint16_t)((a_mu2 + rnd_v) >> sh_v);
-            t_xx[j] = (uint32_t)((a_xx + rnd_v_sq) >> sh_v_sq);
-            t_yy[j] = (uint32_t)((a_yy + rnd_v_sq) >> sh_v_sq);
-            t_xy[j] = (uint32_t)((a_xy + rnd_v_sq) >> sh_v_sq);
+        const void *rows_r[17], *rows_d[17];
+        for (int k = 0; k < fw; ++k) {
+            const int ii = reflect101(i - r + k, h);
+            rows_r[k] = (const uint8_t *)ref + (ptrdiff_t)ii * stride;
+            rows_d[k] = (const uint8_t *)dis + (ptrdiff_t)ii * stride;
         }
-        /* horizontal pass + statistic */
+        orc_vif_vpass(rows_r, rows_d, bps, w, fw, f, a_mu1, a_mu2, a_xx, a_yy, a_xy);
         for (int j = 0; j < w; ++j) {
-            uint32_t a_mu1 = 0, a_mu2 = 0;
-            uint64_t a_xx = 0, a_yy = 0, a_xy = 0;
-            for (int k = 0; k < fw; ++k) {
-                int jj = reflect101(j - r + k, w);
-                a_mu1 += f[k] * (uint32_t)t_mu1[jj];
-                a_mu2 += f[k] * (uint32_t)t_mu2[jj];
-                a_xx += f[k] * (uint64_t)t_xx[jj];
-                a_yy += f[k] * (uint64_t)t_yy[jj];
-                a_xy += f[k] * (uint64_t)t_xy[jj];
-            }
-            uint32_t mu1_sq = (uint32_t)((((uint64_t)a_mu1 * a_mu1) + 2147483648ull) >> 32);
-            uint32_t mu2_sq = (uint32_t)((((uint64_t)a_mu2 * a_mu2) + 2147483648ull) >> 32);
-            uint32_t mu1_mu2 = (uint32_t)((((uint64_t)a_mu1 * a_mu2) + 2147483648ull) >> 32);
-            uint32_t xx = (uint32_t)((a_xx + 32768) >> 16);
-            uint32_t yy = (uint32_t)((a_yy + 32768) >> 16);
-            uint32_t xy = (uint32_t)((a_xy + 32768) >> 16);
+            t_mu1[r + j] = (uint16_t)((a_mu1[j] + rnd_v) >> sh_v);
+            t_mu2[r + j] = (uint16_t)((a_mu2[j] + rnd_v) >> sh_v);
+            t_xx[r + j] = (uint32_t)((a_xx[j] + rnd_v_sq) >> sh_v_sq);
+            t_yy[r + j] = (uint32_t)((a_yy[j] + rnd_v_sq) >> sh_v_sq);
+            t_xy[r + j] = (uint32_t)((a_xy[j] + rnd_v_sq) >> sh_v_sq);
+        }
+        ORC_REFLECT_BORDER(t_mu1, w, r) ORC_REFLECT_BORDER(t_mu2, w, r)
+        ORC_REFLECT_BORDER(t_xx, w, r) ORC_REFLECT_BORDER(t_yy, w, r) ORC_REFLECT_BORDER(t_xy, w, r)
+        /* horizontal pass (the accumulator buffers are free again) + statistic */
+        orc_vif_hpass(t_mu1, t_mu2, t_xx, t_yy, t_xy, w, fw, f, a_mu1, a_mu2, a_xx, a_yy, a_xy);
+        for (int j = 0; j < w; ++j) {
+            const uint32_t h_mu1 = a_mu1[j], h_mu2 = a_mu2[j];
+            uint32_t mu1_sq = (uint32_t)((((uint64_t)h_mu1 * h_mu1) + 2147483648ull) >> 32);
+            uint32_t mu2_sq = (uint32_t)((((uint64_t)h_mu2 * h_mu2) + 2147483648ull) >> 32);
+            uint32_t mu1_mu2 = (uint32_t)((((uint64_t)h_mu1 * h_mu2) + 2147483648ull) >> 32);
+            uint32_t xx = (uint32_t)((a_xx[j] + 32768) >> 16);
+            uint32_t yy = (uint32_t)((a_yy[j] + 32768) >> 16);
+            uint32_t xy = (uint32_t)((a_xy[j] + 32768) >> 16);
             int32_t sigma1_sq = (int32_t)(xx - mu1_sq);
             int32_t sigma2_sq = (int32_t)(yy - mu2_sq);
             int32_t sigma12 = (int32_t)(xy - mu1_mu2);
@@ -245,6 +296,21 @@ static void vif_statistic(const void *ref, const void *dis, int src_bpc, ptrdiff
         }
     }
     free(t_mu1); free(t_mu2); free(t_xx); free(t_yy); free(t_xy);
+    free(a_mu1); free(a_mu2); free(a_xx); free(a_yy); free(a_xy);
+}
+
+#define ORC_VSUB(T)                                                                             \
+    for (int k = 0; k < fw; ++k) {                                                              \
+        const T *xr = (const T *)rows_r[k], *yr = (const T *)rows_d[k];                         \
+        const uint32_t fk = f[k];                                                               \
+        for (int j = 0; j < w; ++j) { ar[j] += fk * (uint32_t)xr[j]; ad[j] += fk * (uint32_t)yr[j]; } \
+    }
+
+ORC_SIMD void orc_vif_vsub(const void *const *rows_r, const void *const *rows_d, int bytes_per_sample, int w, int fw,
+                           const uint16_t *f, uint32_t *ar, uint32_t *ad)
+{
+    memset(ar, 0, sizeof(uint32_t) * w); memset(ad, 0, sizeof(uint32_t) * w);
+    if (bytes_per_sample == 1) { ORC_VSUB(uint8_t) } else { ORC_VSUB(uint16_t) }
 }
 
 /* Filter the level with the NEXT scale's table (V then H) and keep even rows/cols. */
@@ -257,33 +323,37 @@ static void vif_subsample(const void *ref, const void *dis, int src_bpc, ptrdiff
     int sh_v; uint32_t rnd_v;
     if (next_scale == 1) { sh_v = pic_bpc; rnd_v = 1u << (pic_bpc - 1); }
     else { sh_v = 16; rnd_v = 32768; }
-    uint16_t *tr = malloc(sizeof(uint16_t) * w), *td = malloc(sizeof(uint16_t) * w);
+    const int bps = src_bpc == 8 ? 1 : 2;
+    const size_t pw = (size_t)w + 2 * r;
+    uint16_t *tr = malloc(sizeof(uint16_t) * pw), *td = malloc(sizeof(uint16_t) * pw);
+    uint32_t *ar = malloc(sizeof(uint32_t) * w), *ad = malloc(sizeof(uint32_t) * w);
     const int ow = w / 2, oh = h / 2;
     for (int oi = 0; oi < oh; ++oi) {
         const int i = 2 * oi;
-        for (int j = 0; j < w; ++j) {
-            uint32_t ar = 0, ad = 0;
-            for (int k = 0; k < fw; ++k) {
-                int ii = reflect101(i - r + k, h);
-                ar += f[k] * px(ref, src_bpc, stride, ii, j);
-                ad += f[k] * px(dis, src_bpc, stride, ii, j);
-            }
-            tr[j] = (uint16_t)((ar + rnd_v) >> sh_v);
-            td[j] = (uint16_t)((ad + rnd_v) >> sh_v);
+        const void *rows_r[17], *rows_d[17];
+        for (int k = 0; k < fw; ++k) {
+            const int ii = reflect101(i - r + k, h);
+            rows_r[k] = (const uint8_t *)ref + (ptrdiff_t)ii * stride;
+            rows_d[k] = (const uint8_t *)dis + (ptrdiff_t)ii * stride;
         }
+        orc_vif_vsub(rows_r, rows_d, bps, w, fw, f, ar, ad);
+        for (int j = 0; j < w; ++j) {
+            tr[r + j] = (uint16_t)((ar[j] + rnd_v) >> sh_v);
+            td[r + j] = (uint16_t)((ad[j] + rnd_v) >> sh_v);
+        }
+        ORC_REFLECT_BORDER(tr, w, r) ORC_REFLECT_BORDER(td, w, r)
         for (int oj = 0; oj < ow; ++oj) {
             const int j = 2 * oj;
-            uint32_t ar = 0, ad = 0;
+            uint32_t sr = 0, sd = 0;
             for (int k = 0; k < fw; ++k) {
-                int jj = reflect101(j - r + k, w);
-                ar += f[k] * (uint32_t)tr[jj];
-                ad += f[k] * (uint32_t)td[jj];
+                sr += f[k] * (uint32_t)tr[j + k];
+                sd += f[k] * (uint32_t)td[j + k];
             }
-            oref[(size_t)oi * ow + oj] = (uint16_t)((ar + 32768) >> 16);
-            odis[(size_t)oi * ow + oj] = (uint16_t)((ad + 32768) >> 16);
+            oref[(size_t)oi * ow + oj] = (uint16_t)((sr + 32768) >> 16);
+            odis[(size_t)oi * ow + oj] = (uint16_t)((sd + 32768) >> 16);
         }
     }
-    free(tr); free(td);
+    free(tr); free(td); free(ar); free(ad);
 }
 
 /* Derived per-scale num/den: stored through float like libvmaf's VifScore {float num, den}. */
