@@ -61,22 +61,35 @@ ORC_API const float *orc_f_vif_filter(int scale) { return vif_ftab[scale]; }
 #define ORC_SIMD
 #endif
 
+#define ORC_FBLK 32          /* pixels per block: the accumulators stay in vector registers across the tap loop */
+
 ORC_SIMD void orc_f_fir_rows(const float *const *rows, const float *f, int fw, int w, float *restrict out)
 {
-    for (int j = 0; j < w; ++j) out[j] = 0.0f;
-    for (int k = 0; k < fw; ++k) {
-        const float *restrict v = rows[k];
-        const float fk = f[k];
-        for (int j = 0; j < w; ++j) out[j] += fk * v[j];
+    for (int j0 = 0; j0 < w; j0 += ORC_FBLK) {
+        const int nb = w - j0 < ORC_FBLK ? w - j0 : ORC_FBLK;
+        float acc[ORC_FBLK] = { 0.0f };
+        for (int k = 0; k < fw; ++k) {
+            const float *restrict v = rows[k] + j0;
+            const float fk = f[k];
+            if (nb == ORC_FBLK) { for (int j = 0; j < ORC_FBLK; ++j) acc[j] += fk * v[j]; }
+            else { for (int j = 0; j < nb; ++j) acc[j] += fk * v[j]; }
+        }
+        memcpy(out + j0, acc, sizeof(float) * nb);
     }
 }
 
 ORC_SIMD void orc_f_fir_shift(const float *restrict padded, const float *f, int fw, int w, float *restrict out)
 {
-    for (int j = 0; j < w; ++j) out[j] = 0.0f;
-    for (int k = 0; k < fw; ++k) {
-        const float fk = f[k];
-        for (int j = 0; j < w; ++j) out[j] += fk * padded[j + k];
+    for (int j0 = 0; j0 < w; j0 += ORC_FBLK) {
+        const int nb = w - j0 < ORC_FBLK ? w - j0 : ORC_FBLK;
+        float acc[ORC_FBLK] = { 0.0f };
+        for (int k = 0; k < fw; ++k) {
+            const float *restrict v = padded + j0 + k;
+            const float fk = f[k];
+            if (nb == ORC_FBLK) { for (int j = 0; j < ORC_FBLK; ++j) acc[j] += fk * v[j]; }
+            else { for (int j = 0; j < nb; ++j) acc[j] += fk * v[j]; }
+        }
+        memcpy(out + j0, acc, sizeof(float) * nb);
     }
 }
 
@@ -411,23 +424,18 @@ static float *decimate_lpf2(const float *img, int w, int h, int *ow, int *oh)
     return dst;
 }
 
-/* valid 11x11 separable Gaussian (horizontal then vertical) */
+/* valid 11x11 separable Gaussian (horizontal then vertical); the row-wise FIR helpers of the VIF section: every output is
+ * still s = 0, s += sample * g[u] for u = 0 .. 10 in float (multiplication commutes, so the operand order is immaterial) */
 static void gauss_valid(const float *img, int w, int h, float *dst)
 {
     int vw = w - 10, vh = h - 10;
     float *tmp = malloc(4 * (size_t)vw * h);
-    for (int y = 0; y < h; ++y)
-        for (int x = 0; x < vw; ++x) {
-            float s = 0;
-            for (int u = 0; u < 11; ++u) s += img[(size_t)y * w + x + u] * g_gauss11[u];
-            tmp[(size_t)y * vw + x] = s;
-        }
-    for (int y = 0; y < vh; ++y)
-        for (int x = 0; x < vw; ++x) {
-            float s = 0;
-            for (int v = 0; v < 11; ++v) s += tmp[(size_t)(y + v) * vw + x] * g_gauss11[v];
-            dst[(size_t)y * vw + x] = s;
-        }
+    for (int y = 0; y < h; ++y) orc_f_fir_shift(img + (size_t)y * w, g_gauss11, 11, vw, tmp + (size_t)y * vw);
+    for (int y = 0; y < vh; ++y) {
+        const float *rows[11];
+        for (int v = 0; v < 11; ++v) rows[v] = tmp + (size_t)(y + v) * vw;
+        orc_f_fir_rows(rows, g_gauss11, 11, vw, dst + (size_t)y * vw);
+    }
     free(tmp);
 }
 

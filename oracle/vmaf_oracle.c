@@ -164,25 +164,43 @@ enum { V_NUM_LOG, V_DEN_LOG, V_NUM_NONLOG, V_DEN_NONLOG, V_X, V_X2, V_CNT };
 #define ORC_SIMD
 #endif
 
-/* a[j] += f * row[j] for the two pictures, and the three second-moment products */
+/* a[j] = sum_k f[k] * row_k[j] for the two pictures, and the three second-moment products.  Blocks of ORC_BLK pixels keep
+ * the five accumulators in vector registers across the tap loop (a row-long accumulator array would go through L2 once
+ * per tap). */
+#define ORC_BLK 32
 #define ORC_VPASS(T)                                                                            \
-    for (int k = 0; k < fw; ++k) {                                                              \
-        const T *xr = (const T *)rows_r[k], *yr = (const T *)rows_d[k];                         \
-        const uint32_t fk = f[k];                                                               \
-        for (int j = 0; j < w; ++j) {                                                           \
-            const uint32_t x = xr[j], y = yr[j];                                                \
-            const uint32_t fx = fk * x, fy = fk * y;                                            \
-            a_mu1[j] += fx; a_mu2[j] += fy;                                                     \
-            a_xx[j] += (uint64_t)fx * x; a_yy[j] += (uint64_t)fy * y; a_xy[j] += (uint64_t)fx * y; \
+    for (int j0 = 0; j0 < w; j0 += ORC_BLK) {                                                   \
+        const int nb = w - j0 < ORC_BLK ? w - j0 : ORC_BLK;                                     \
+        uint32_t m1[ORC_BLK] = { 0 }, m2[ORC_BLK] = { 0 };                                      \
+        uint64_t sxx[ORC_BLK] = { 0 }, syy[ORC_BLK] = { 0 }, sxy[ORC_BLK] = { 0 };              \
+        for (int k = 0; k < fw; ++k) {                                                          \
+            const T *xr = (const T *)rows_r[k] + j0, *yr = (const T *)rows_d[k] + j0;           \
+            const uint32_t fk = f[k];                                                           \
+            if (nb == ORC_BLK) {                                                                \
+                for (int j = 0; j < ORC_BLK; ++j) {                                             \
+                    const uint32_t x = xr[j], y = yr[j];                                        \
+                    const uint32_t fx = fk * x, fy = fk * y;                                    \
+                    m1[j] += fx; m2[j] += fy;                                                   \
+                    sxx[j] += (uint64_t)fx * x; syy[j] += (uint64_t)fy * y; sxy[j] += (uint64_t)fx * y; \
+                }                                                                               \
+            } else {                                                                            \
+                for (int j = 0; j < nb; ++j) {                                                  \
+                    const uint32_t x = xr[j], y = yr[j];                                        \
+                    const uint32_t fx = fk * x, fy = fk * y;                                    \
+                    m1[j] += fx; m2[j] += fy;                                                   \
+                    sxx[j] += (uint64_t)fx * x; syy[j] += (uint64_t)fy * y; sxy[j] += (uint64_t)fx * y; \
+                }                                                                               \
+            }                                                                                   \
         }                                                                                       \
+        memcpy(a_mu1 + j0, m1, sizeof(uint32_t) * nb); memcpy(a_mu2 + j0, m2, sizeof(uint32_t) * nb); \
+        memcpy(a_xx + j0, sxx, sizeof(uint64_t) * nb); memcpy(a_yy + j0, syy, sizeof(uint64_t) * nb); \
+        memcpy(a_xy + j0, sxy, sizeof(uint64_t) * nb);                                          \
     }
 
 ORC_SIMD void orc_vif_vpass(const void *const *rows_r, const void *const *rows_d, int bytes_per_sample, int w, int fw,
                             const uint16_t *f, uint32_t *a_mu1, uint32_t *a_mu2, uint64_t *a_xx, uint64_t *a_yy,
                             uint64_t *a_xy)
 {
-    memset(a_mu1, 0, sizeof(uint32_t) * w); memset(a_mu2, 0, sizeof(uint32_t) * w);
-    memset(a_xx, 0, sizeof(uint64_t) * w); memset(a_yy, 0, sizeof(uint64_t) * w); memset(a_xy, 0, sizeof(uint64_t) * w);
     if (bytes_per_sample == 1) { ORC_VPASS(uint8_t) } else { ORC_VPASS(uint16_t) }
 }
 
@@ -191,17 +209,29 @@ ORC_SIMD void orc_vif_hpass(const uint16_t *p_mu1, const uint16_t *p_mu2, const 
                             const uint32_t *p_xy, int w, int fw, const uint16_t *f, uint32_t *h_mu1, uint32_t *h_mu2,
                             uint64_t *h_xx, uint64_t *h_yy, uint64_t *h_xy)
 {
-    memset(h_mu1, 0, sizeof(uint32_t) * w); memset(h_mu2, 0, sizeof(uint32_t) * w);
-    memset(h_xx, 0, sizeof(uint64_t) * w); memset(h_yy, 0, sizeof(uint64_t) * w); memset(h_xy, 0, sizeof(uint64_t) * w);
-    for (int k = 0; k < fw; ++k) {
-        const uint32_t fk = f[k];
-        for (int j = 0; j < w; ++j) {
-            h_mu1[j] += fk * (uint32_t)p_mu1[j + k];
-            h_mu2[j] += fk * (uint32_t)p_mu2[j + k];
-            h_xx[j] += (uint64_t)fk * p_xx[j + k];
-            h_yy[j] += (uint64_t)fk * p_yy[j + k];
-            h_xy[j] += (uint64_t)fk * p_xy[j + k];
+    for (int j0 = 0; j0 < w; j0 += ORC_BLK) {
+        const int nb = w - j0 < ORC_BLK ? w - j0 : ORC_BLK;
+        uint32_t m1[ORC_BLK] = { 0 }, m2[ORC_BLK] = { 0 };
+        uint64_t sxx[ORC_BLK] = { 0 }, syy[ORC_BLK] = { 0 }, sxy[ORC_BLK] = { 0 };
+        for (int k = 0; k < fw; ++k) {
+            const uint32_t fk = f[k];
+            const uint16_t *q1 = p_mu1 + j0 + k, *q2 = p_mu2 + j0 + k;
+            const uint32_t *qxx = p_xx + j0 + k, *qyy = p_yy + j0 + k, *qxy = p_xy + j0 + k;
+            if (nb == ORC_BLK) {
+                for (int j = 0; j < ORC_BLK; ++j) {
+                    m1[j] += fk * (uint32_t)q1[j]; m2[j] += fk * (uint32_t)q2[j];
+                    sxx[j] += (uint64_t)fk * qxx[j]; syy[j] += (uint64_t)fk * qyy[j]; sxy[j] += (uint64_t)fk * qxy[j];
+                }
+            } else {
+                for (int j = 0; j < nb; ++j) {
+                    m1[j] += fk * (uint32_t)q1[j]; m2[j] += fk * (uint32_t)q2[j];
+                    sxx[j] += (uint64_t)fk * qxx[j]; syy[j] += (uint64_t)fk * qyy[j]; sxy[j] += (uint64_t)fk * qxy[j];
+                }
+            }
         }
+        memcpy(h_mu1 + j0, m1, sizeof(uint32_t) * nb); memcpy(h_mu2 + j0, m2, sizeof(uint32_t) * nb);
+        memcpy(h_xx + j0, sxx, sizeof(uint64_t) * nb); memcpy(h_yy + j0, syy, sizeof(uint64_t) * nb);
+        memcpy(h_xy + j0, sxy, sizeof(uint64_t) * nb);
     }
 }
 
