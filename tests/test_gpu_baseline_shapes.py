@@ -78,7 +78,7 @@ def test_float_extractors_at_high_bit_depth_full_size(w, h, bpc, n):
 
 def test_golden_fixtures_at_baseline_shapes():
     """tests/golden/fullsize_oracle.json: the raw integer accumulators of one 1080p 8-bit and one 2160p 10-bit pair
-    (oracle outputs, written by tools/make_golden.py) straight against the kernels."""
+    (oracle outputs, written by tests/tools/make_golden.py) straight against the kernels."""
     import json
     import os
     path = os.path.join(os.path.dirname(__file__), "golden", "fullsize_oracle.json")

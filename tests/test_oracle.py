@@ -1,5 +1,5 @@
 """CPU tests of the oracle itself (no GPU): regression vectors under tests/golden/ (made by
-tools/make_golden.py from the oracle -- the reference ships no golden vectors), and the pins
+tests/tools/make_golden.py from the oracle -- the reference ships no golden vectors), and the pins
 SURVEY.md §8c lists: filter tables, identical-pair and static-clip invariants, monotonicity."""
 import glob
 import json

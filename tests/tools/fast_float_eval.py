@@ -4,7 +4,7 @@ Writes a markdown table (default gpurun_out/r02_fast_float.md).  North-star tole
 import multiprocessing as mp
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def _oracle_job(a):
@@ -25,7 +25,7 @@ def main():
     cases = [(3, 176, 144, 8, 3), (3, 322, 242, 8, 2), (3, 333, 251, 8, 2), (3, 640, 360, 8, 5), (3, 416, 240, 10, 3),
              (3, 960, 540, 8, 1), (4, 352, 288, 8, 2), (4, 1280, 720, 8, 2), (4, 335, 253, 8, 2), (21, 640, 360, 8, 6),
              (100, 1920, 1080, 8, 64)]
-    lines = ["# fast_float vs the oracle (tools/fast_float_eval.py)", "",
+    lines = ["# fast_float vs the oracle (tests/tools/fast_float_eval.py)", "",
              "`fast` = bv_opts.fast_float (FMA-contracted, folded-tap stencils); `faithful` = the default build (libvmaf's scalar "
              "operation order).  Deltas are against oracle/ (CPU restatement) through the same SVR (vmaf_float_v0.6.1).", "",
              "clip | frames | max abs dVMAF/frame faithful | fast | pooled-mean dVMAF faithful | fast | max abs d(feature) fast | d float_ssim fast | d float_ms_ssim fast",

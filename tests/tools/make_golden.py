@@ -4,14 +4,16 @@ These are NOT outputs of the reference (ffmpeg + libvmaf cannot run in this imag
 golden vectors); they freeze the oracle so that an accidental change to oracle/ or to the
 synthetic generator shows up, and give the GPU tests a second, file-based comparison point.
 
-    python tools/make_golden.py"""
+    python tests/tools/make_golden.py
+
+Lives under tests/ because it imports the oracle (only tests/, smoke() and bench.py's CPU legs may)."""
 import json
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 from pqa2_b200 import synth  # noqa: E402
