@@ -401,24 +401,33 @@ static float *decimate_box(const float *img, int w, int h, int f, int *ow, int *
     return dst;
 }
 
-/* _iqa_decimate by 2 with the separable 9-tap low-pass (horizontal then vertical), symmetric borders */
+/* _iqa_decimate by 2 with the separable 9-tap low-pass (horizontal then vertical), symmetric borders.  The horizontal pass
+ * reads a row copy that carries its 4-sample symmetric border (no index arithmetic per tap); the vertical pass is the
+ * row-wise FIR helper.  Per output still sum = 0, sum += sample * g[u] for u = 0 .. 8 in float. */
 static float *decimate_lpf2(const float *img, int w, int h, int *ow, int *oh)
 {
     int dw = w / 2 + (w & 1), dh = h / 2 + (h & 1);
     float *tmp = malloc(4 * (size_t)dw * h);
-    for (int y = 0; y < h; ++y)
+    float *row = malloc(4 * ((size_t)w + 16));
+    for (int y = 0; y < h; ++y) {
+        const float *src = img + (size_t)y * w;
+        memcpy(row + 4, src, 4 * (size_t)w);
+        for (int m = 1; m <= 4; ++m) row[4 - m] = src[sym(-m, w)];
+        for (int m = 0; m < 8; ++m) row[4 + w + m] = src[sym(w + m, w)];
         for (int x = 0; x < dw; ++x) {
+            const float *q = row + 2 * x;
             float sum = 0;
-            for (int u = 0; u < 9; ++u) sum += img[(size_t)y * w + sym(2 * x - 4 + u, w)] * g_lpf9[u];
+            for (int u = 0; u < 9; ++u) sum += q[u] * g_lpf9[u];
             tmp[(size_t)y * dw + x] = sum;
         }
+    }
+    free(row);
     float *dst = malloc(4 * (size_t)dw * dh);
-    for (int y = 0; y < dh; ++y)
-        for (int x = 0; x < dw; ++x) {
-            float sum = 0;
-            for (int v = 0; v < 9; ++v) sum += tmp[(size_t)sym(2 * y - 4 + v, h) * dw + x] * g_lpf9[v];
-            dst[(size_t)y * dw + x] = sum;
-        }
+    for (int y = 0; y < dh; ++y) {
+        const float *rows[9];
+        for (int v = 0; v < 9; ++v) rows[v] = tmp + (size_t)sym(2 * y - 4 + v, h) * dw;
+        orc_f_fir_rows(rows, g_lpf9, 9, dw, dst + (size_t)y * dw);
+    }
     free(tmp);
     *ow = dw; *oh = dh;
     return dst;
