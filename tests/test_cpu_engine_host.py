@@ -333,3 +333,52 @@ def test_long_clip_on_several_devices_is_dealt_in_chunks(fake):
     assert len(fake.instances) == 2                                  # one context per device, reused from chunk to chunk
     fixed = engine.analyze(Clip(n), model, _opt(devices=(0, 0), dynamic_chunk=0))
     assert [fr["metrics"] for fr in fixed["frames"]] == [fr["metrics"] for fr in one["frames"]]
+
+
+def test_container_pair_is_decoded_in_step(fake, tmp_path):
+    """Compressed inputs: one sequential decoder per file (each with libavcodec's frame threads: decoding the two files on
+    two host threads was measured, +5 %, and left out); every frame pair must reach the extractor in order and in step,
+    and a distorted stream that is shorter than its container claims ends the analysis there (ffmpeg + libvmaf stop at
+    the shorter input)."""
+    cv2 = pytest.importorskip("cv2")
+    from pqa2_b200 import yuvio
+    w, h = 64, 48
+
+    def write(path, levels):
+        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 25, (w, h))
+        if not wr.isOpened():
+            pytest.skip("cv2 cannot encode mp4v here")
+        for v in levels:
+            wr.write(np.full((h, w, 3), v, np.uint8))
+        wr.release()
+
+    n = 20
+    ref_p, dis_p = str(tmp_path / "ref.mp4"), str(tmp_path / "dis.mp4")
+    write(ref_p, [20 + 10 * i for i in range(n)])
+    write(dis_p, [25 + 10 * i for i in range(n)])
+    ri, di = yuvio.probe(ref_p), yuvio.probe(dis_p)
+    assert ri.decoder != "raw" and ri.nb_frames == n
+    src = engine.FileSource(ri, di)
+    assert src.sequential and not src.parallel_reads
+    seen = []
+    real_submit = FakeExtractor.submit
+
+    def submit(self, frame_index, ref_planes, dis_planes, flags=0):
+        seen.append((int(frame_index), int(ref_planes[0][h // 2, w // 2]), int(dis_planes[0][h // 2, w // 2])))
+        real_submit(self, frame_index, ref_planes, dis_planes, flags)
+
+    FakeExtractor.submit = submit
+    try:
+        res = engine.analyze(src, M.resolve_model("vmaf_v0.6.1"), _opt(devices=(0,)))
+        assert len(fake.instances) == 1 and len(res["frames"]) == n
+        assert [s[0] for s in seen] == list(range(n))
+        for idx, r, d in seen:
+            # limited-range luma of a flat grey picture: 16 + 219 / 255 * level, within a couple of code values
+            assert abs(r - (16 + (20 + 10 * idx) * 219 / 255)) < 3 and abs(d - (16 + (25 + 10 * idx) * 219 / 255)) < 3
+        # the distorted container claims more frames than it holds
+        di.nb_frames = ri.nb_frames = n + 7
+        seen.clear()
+        cut = engine.analyze(engine.FileSource(ri, di), M.resolve_model("vmaf_v0.6.1"), _opt())
+        assert len(cut["frames"]) == n and [s[0] for s in seen] == list(range(n))
+    finally:
+        FakeExtractor.submit = real_submit
